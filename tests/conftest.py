@@ -1,0 +1,37 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG_ROOT = os.path.join(ROOT, "fast-poisson-image-editing_b200")
+for p in (ROOT, PKG_ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    path = os.path.join(ROOT, "tests", "golden", "fpie_numpy_golden.npz")
+    with np.load(path) as z:
+        return {k: z[k] for k in z.files}
+
+
+GOLDEN_CASES = ("smoke6", "rng24", "ring_off", "holes_full", "disk_sat")
+MODES = ("max", "src", "avg")
+
+
+def golden_case(golden, name):
+    return dict(
+        src=golden[f"{name}/src"],
+        mask=golden[f"{name}/mask"],
+        tgt=golden[f"{name}/tgt"],
+        off_src=tuple(int(v) for v in golden[f"{name}/off_src"]),
+        off_tgt=tuple(int(v) for v in golden[f"{name}/off_tgt"]),
+        steps=[int(v) for v in golden[f"{name}/steps"]],
+    )
