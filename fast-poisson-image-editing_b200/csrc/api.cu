@@ -1,0 +1,218 @@
+// extern "C" surface of libfpie_b200.so -- see include/fpie_b200.h.
+#include "fpie_b200.h"
+
+#include <cstring>
+#include <string>
+
+#include "equ_solver.cuh"
+#include "grid_solver.cuh"
+
+struct fpie_b200_grid {
+  fpie::GridSolver impl;
+  fpie_b200_grid(int d, cudaStream_t s, int k, int v) : impl(d, s, k, v) {}
+};
+struct fpie_b200_equ {
+  fpie::EquSolver impl;
+  fpie_b200_equ(int d, cudaStream_t s, int z) : impl(d, s, z) {}
+};
+
+namespace {
+thread_local std::string g_last_error;
+
+template <typename F>
+int guarded(F &&body) {
+  try {
+    body();
+    return 0;
+  } catch (const fpie::Error &e) {
+    g_last_error = e.what();
+    return 1;
+  } catch (const std::bad_alloc &) {
+    g_last_error = "out of host memory";
+    return 2;
+  } catch (const std::exception &e) {
+    g_last_error = e.what();
+    return 3;
+  }
+}
+
+#define NEED(h)                                             \
+  if (!(h)) {                                               \
+    g_last_error = "fpie_b200: null solver handle";         \
+    return 4;                                               \
+  }
+}  // namespace
+
+#define API extern "C" __attribute__((visibility("default")))
+
+API int fpie_b200_abi_version(void) { return FPIE_B200_ABI_VERSION; }
+API const char *fpie_b200_last_error(void) { return g_last_error.c_str(); }
+
+API int fpie_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+API int fpie_b200_device_info(int device, char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor) {
+  return guarded([&] {
+    cudaDeviceProp prop{};
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (name && name_len > 0) {
+      strncpy(name, prop.name, (size_t)name_len - 1);
+      name[name_len - 1] = 0;
+    }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+  });
+}
+
+// ---- GridSolver -----------------------------------------------------------
+API int fpie_b200_grid_create(int device, void *stream, int block_k, int variant, fpie_b200_grid **out) {
+  if (!out) {
+    g_last_error = "fpie_b200_grid_create: null output";
+    return 4;
+  }
+  *out = nullptr;
+  return guarded([&] { *out = new fpie_b200_grid(device, (cudaStream_t)stream, block_k, variant); });
+}
+API int fpie_b200_grid_destroy(fpie_b200_grid *g) {
+  return guarded([&] { delete g; });
+}
+API int fpie_b200_grid_reset(fpie_b200_grid *g, int n, int m, const int32_t *mask, int64_t mask_row_stride,
+                             int64_t mask_col_stride, const float *tgt, const float *grad) {
+  NEED(g);
+  return guarded([&] { g->impl.reset(n, m, mask, mask_row_stride, mask_col_stride, tgt, grad); });
+}
+API int fpie_b200_grid_step(fpie_b200_grid *g, int iters, uint8_t *out_img, float *out_err3) {
+  NEED(g);
+  return guarded([&] { g->impl.step(iters, out_img, out_err3); });
+}
+API int fpie_b200_grid_state(fpie_b200_grid *g, float *out_state) {
+  NEED(g);
+  return guarded([&] { g->impl.state(out_state); });
+}
+API int fpie_b200_grid_sweeps_async(fpie_b200_grid *g, int iters) {
+  NEED(g);
+  return guarded([&] { g->impl.sweeps_async(iters); });
+}
+API int fpie_b200_grid_finish_async(fpie_b200_grid *g) {
+  NEED(g);
+  return guarded([&] { g->impl.finish_async(); });
+}
+API int fpie_b200_grid_sync(fpie_b200_grid *g) {
+  NEED(g);
+  return guarded([&] { g->impl.sync(); });
+}
+API int fpie_b200_grid_fetch(fpie_b200_grid *g, uint8_t *out_img, float *out_err3) {
+  NEED(g);
+  return guarded([&] { g->impl.fetch(out_img, out_err3); });
+}
+API int fpie_b200_grid_info(fpie_b200_grid *g, int64_t *unknowns, int64_t *launches, int *block_k,
+                            int64_t *active_tiles, int64_t *total_tiles) {
+  NEED(g);
+  return guarded([&] {
+    const fpie::GridStats &s = g->impl.stats();
+    if (unknowns) *unknowns = s.unknowns;
+    if (launches) *launches = s.launches;
+    if (block_k) *block_k = g->impl.block_k();
+    if (active_tiles) *active_tiles = s.active_tiles;
+    if (total_tiles) *total_tiles = s.total_tiles;
+  });
+}
+API int fpie_b200_grid_reset_from_images(fpie_b200_grid *g, const uint8_t *src, int sh, int sw, const uint8_t *mask,
+                                         int mh, int mw, int mc, const uint8_t *tgt, int th, int tw, int h0, int w0,
+                                         int h1, int w1, int grad_mode, int64_t *out_n, int32_t *out_box4) {
+  NEED(g);
+  return guarded([&] {
+    g->impl.reset_from_images(src, sh, sw, mask, mh, mw, mc, tgt, th, tw, h0, w0, h1, w1, grad_mode, out_n, out_box4);
+  });
+}
+API int fpie_b200_grid_band_view(fpie_b200_grid *g, int which_buffer, float **dev_base, int64_t *plane_stride,
+                                 int64_t *row_pitch, int *pad_rows, int *pad_cols) {
+  NEED(g);
+  return guarded([&] { g->impl.band_view(which_buffer, dev_base, plane_stride, row_pitch, pad_rows, pad_cols); });
+}
+API int fpie_b200_grid_band_current(fpie_b200_grid *g, int *which_buffer) {
+  NEED(g);
+  return guarded([&] {
+    if (which_buffer) *which_buffer = g->impl.current();
+  });
+}
+API int fpie_b200_grid_set_row_window(fpie_b200_grid *g, int row_lo, int row_hi) {
+  NEED(g);
+  return guarded([&] { g->impl.set_row_window(row_lo, row_hi); });
+}
+
+// ---- EquSolver ------------------------------------------------------------
+API int fpie_b200_equ_create(int device, void *stream, int block_size, fpie_b200_equ **out) {
+  if (!out) {
+    g_last_error = "fpie_b200_equ_create: null output";
+    return 4;
+  }
+  *out = nullptr;
+  return guarded([&] { *out = new fpie_b200_equ(device, (cudaStream_t)stream, block_size); });
+}
+API int fpie_b200_equ_destroy(fpie_b200_equ *e) {
+  return guarded([&] { delete e; });
+}
+API int fpie_b200_equ_partition(fpie_b200_equ *e, int n, int m, const int32_t *mask, int64_t mask_row_stride,
+                                int64_t mask_col_stride, int32_t *out_ids) {
+  NEED(e);
+  return guarded([&] { e->impl.partition(n, m, mask, mask_row_stride, mask_col_stride, out_ids); });
+}
+API int fpie_b200_equ_reset(fpie_b200_equ *e, int64_t N, const int32_t *A, const float *X, const float *B) {
+  NEED(e);
+  return guarded([&] { e->impl.reset(N, A, X, B); });
+}
+API int fpie_b200_equ_step(fpie_b200_equ *e, int iters, uint8_t *out_img, float *out_err3) {
+  NEED(e);
+  return guarded([&] { e->impl.step(iters, out_img, out_err3); });
+}
+API int fpie_b200_equ_state(fpie_b200_equ *e, float *out_state) {
+  NEED(e);
+  return guarded([&] { e->impl.state(out_state); });
+}
+API int fpie_b200_equ_sweeps_async(fpie_b200_equ *e, int iters) {
+  NEED(e);
+  return guarded([&] { e->impl.sweeps_async(iters); });
+}
+API int fpie_b200_equ_finish_async(fpie_b200_equ *e) {
+  NEED(e);
+  return guarded([&] { e->impl.finish_async(); });
+}
+API int fpie_b200_equ_sync(fpie_b200_equ *e) {
+  NEED(e);
+  return guarded([&] { e->impl.sync(); });
+}
+API int fpie_b200_equ_fetch(fpie_b200_equ *e, uint8_t *out_img, float *out_err3) {
+  NEED(e);
+  return guarded([&] { e->impl.fetch(out_img, out_err3); });
+}
+API int fpie_b200_equ_info(fpie_b200_equ *e, int64_t *unknowns, int64_t *launches) {
+  NEED(e);
+  return guarded([&] {
+    if (unknowns) *unknowns = e->impl.stats().unknowns;
+    if (launches) *launches = e->impl.stats().launches;
+  });
+}
+API int fpie_b200_equ_reset_from_images(fpie_b200_equ *e, const uint8_t *src, int sh, int sw, const uint8_t *mask,
+                                        int mh, int mw, int mc, const uint8_t *tgt, int th, int tw, int h0, int w0,
+                                        int h1, int w1, int grad_mode, int64_t *out_n, int32_t *out_box4) {
+  NEED(e);
+  return guarded([&] {
+    e->impl.reset_from_images(src, sh, sw, mask, mh, mw, mc, tgt, th, tw, h0, w0, h1, w1, grad_mode, out_n, out_box4);
+  });
+}
+API int fpie_b200_equ_step_paste(fpie_b200_equ *e, int iters, uint8_t *out_crop, float *out_err3) {
+  NEED(e);
+  return guarded([&] { e->impl.step_paste(iters, out_crop, out_err3); });
+}
+API int fpie_b200_equ_system(fpie_b200_equ *e, int32_t *out_A, float *out_X, float *out_B) {
+  NEED(e);
+  return guarded([&] { e->impl.system(out_A, out_X, out_B); });
+}

@@ -1,0 +1,493 @@
+// EquSolver kernels + host driver (sm_100a).
+//
+// Replaces fpie/core/cuda/equ.cu (reference).  Differences in design:
+//   * true Jacobi with ping-pong buffers (fpie/np_solver.py:33-41), not the
+//     reference CUDA backend's racy in-place update (equ.cu:193-197);
+//   * X and B are stored as three channel planes so that the four gathers of a
+//     warp are 128-byte coalesced runs whenever ids are row-major;
+//   * partition is a device prefix scan (equ.cu:36-54 is a serial host loop);
+//   * residual = warp-shuffle + block reduction into fp64 (equ.cu:162-179 is a
+//     single block with a serial tail).
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "equ_solver.cuh"
+#include "prep.cuh"
+
+namespace fpie {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_CHUNK = SCAN_THREADS * SCAN_ITEMS;
+
+// ---------------------------------------------------------------------------
+// partition: inclusive scan of (mask > 0), reduce-then-scan in three launches
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *total) {
+  __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_sums[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t s = (lane < SCAN_THREADS / 32) ? warp_sums[lane] : 0u;
+#pragma unroll
+    for (int o = 1; o < SCAN_THREADS / 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += t;
+    }
+    if (lane < SCAN_THREADS / 32) warp_sums[lane] = s;  // inclusive over warps
+  }
+  __syncthreads();
+  const uint32_t warp_off = (w > 0) ? warp_sums[w - 1] : 0u;
+  if (total) *total = warp_sums[SCAN_THREADS / 32 - 1];
+  __syncthreads();
+  return warp_off + inc - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_count_kernel(const int32_t *__restrict__ mask, long long count, uint32_t *__restrict__ block_sums) {
+  const long long base = (long long)blockIdx.x * SCAN_CHUNK + (long long)threadIdx.x * SCAN_ITEMS;
+  uint32_t c = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i)
+    if (base + i < count) c += mask[base + i] > 0;
+  uint32_t total;
+  block_exclusive_scan(c, &total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// exclusive scan of the block sums, one CTA, carries across chunks
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_block_sums_kernel(uint32_t *__restrict__ block_sums, int nblocks) {
+  uint32_t carry = 0;
+  for (int base = 0; base < nblocks; base += SCAN_THREADS) {
+    const int i = base + threadIdx.x;
+    const uint32_t v = (i < nblocks) ? block_sums[i] : 0u;
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan(v, &total);
+    if (i < nblocks) block_sums[i] = carry + ex;
+    carry += total;
+  }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_write_kernel(const int32_t *__restrict__ mask, long long count, const uint32_t *__restrict__ block_offsets,
+                  int32_t *__restrict__ ids) {
+  const long long base = (long long)blockIdx.x * SCAN_CHUNK + (long long)threadIdx.x * SCAN_ITEMS;
+  uint32_t f[SCAN_ITEMS];
+  uint32_t c = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    f[i] = (base + i < count) ? (mask[base + i] > 0) : 0u;
+    c += f[i];
+  }
+  uint32_t run = block_offsets[blockIdx.x] + block_exclusive_scan(c, nullptr);
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    run += f[i];
+    if (base + i < count) ids[base + i] = (int32_t)run;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// upload helpers
+// ---------------------------------------------------------------------------
+__global__ void rows3_to_planes_kernel(long long N, long long pitch, const float *__restrict__ aos,
+                                       float *__restrict__ dst0, float *__restrict__ dst1) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const float v = aos[i * 3 + ch];
+    dst0[ch * pitch + i] = v;
+    if (dst1) dst1[ch * pitch + i] = v;
+  }
+}
+
+__global__ void planes_to_rows3_kernel(long long N, long long pitch, const float *__restrict__ src,
+                                       float *__restrict__ aos) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) aos[i * 3 + ch] = src[ch * pitch + i];
+}
+
+__global__ void check_index_kernel(long long N, const int4 *__restrict__ A, int *__restrict__ flag) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int4 a = A[i];
+  const bool bad = a.x < 0 || a.y < 0 || a.z < 0 || a.w < 0 || a.x >= N || a.y >= N || a.z >= N || a.w >= N;
+  if (bad) atomicExch(flag, 1);
+}
+
+// ---------------------------------------------------------------------------
+// sweep / residual / output
+// ---------------------------------------------------------------------------
+// X'[i] = ((((B[i] + X[up]) + X[down]) + X[left]) + X[right]) / 4   (np_solver.py:33-41)
+__global__ void __launch_bounds__(1024)
+equ_sweep_kernel(long long N, long long pitch, const int4 *__restrict__ A, const float *__restrict__ B,
+                 const float *__restrict__ xin, float *__restrict__ xout) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int4 a = A[i];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const float *x = xin + ch * pitch;
+    float s = __fadd_rn(B[ch * pitch + i], x[a.x]);
+    s = __fadd_rn(s, x[a.y]);
+    s = __fadd_rn(s, x[a.z]);
+    s = __fadd_rn(s, x[a.w]);
+    xout[ch * pitch + i] = __fmul_rn(s, 0.25f);
+  }
+}
+
+// err[c] = sum_i |((((B + X[up]) + X[down]) + X[left]) + X[right]) - 4 X[i]|   (np_solver.py:42-50)
+__global__ void __launch_bounds__(256)
+equ_residual_kernel(long long N, long long pitch, const int4 *__restrict__ A, const float *__restrict__ B,
+                    const float *__restrict__ x, double *__restrict__ err) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  double v[3] = {0.0, 0.0, 0.0};
+  if (i < N) {
+    const int4 a = A[i];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const float *xc = x + ch * pitch;
+      float s = __fadd_rn(B[ch * pitch + i], xc[a.x]);
+      s = __fadd_rn(s, xc[a.y]);
+      s = __fadd_rn(s, xc[a.z]);
+      s = __fadd_rn(s, xc[a.w]);
+      s = __fsub_rn(s, __fmul_rn(4.0f, xc[i]));
+      v[ch] = (double)fabsf(s);
+    }
+  }
+  __shared__ double partial[3][8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[ch] += __shfl_down_sync(0xffffffffu, v[ch], o);
+    if (lane == 0) partial[ch][w] = v[ch];
+  }
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      double t = (lane < (blockDim.x >> 5)) ? partial[ch][lane] : 0.0;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+      if (lane == 0 && t != 0.0) atomicAdd(&err[ch], t);
+    }
+  }
+}
+
+__device__ __forceinline__ uint8_t clip_byte(float v) { return (uint8_t)__float2uint_rz(fminf(fmaxf(v, 0.f), 255.f)); }
+
+// img[N, 3] u8 (equ.cu:181-187; row 0 is written too, as zeros)
+__global__ void __launch_bounds__(256)
+equ_to_u8_kernel(long long N, long long pitch, const float *__restrict__ x, uint8_t *__restrict__ img) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) img[i * 3 + ch] = clip_byte(x[ch * pitch + i]);
+}
+
+// ---------------------------------------------------------------------------
+// fused Processor-level reset: A / X / B straight from uint8 images
+// (fpie/process.py:227-266)
+// ---------------------------------------------------------------------------
+__global__ void crop_flags_kernel(BlendImages b, int32_t *__restrict__ flags, uint8_t *__restrict__ canvas) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)b.n * b.m) return;
+  const int i = (int)(idx / b.m), j = (int)(idx % b.m);
+  flags[idx] = canonical_mask_at(b, b.x0 + i, b.y0 + j) ? 1 : 0;
+  const long long tp = ((long long)(b.h1 + b.x0 + i) * b.tw + (b.w1 + b.y0 + j)) * 3;
+  canvas[idx * 3 + 0] = b.tgt[tp + 0];
+  canvas[idx * 3 + 1] = b.tgt[tp + 1];
+  canvas[idx * 3 + 2] = b.tgt[tp + 2];
+}
+
+__global__ void __launch_bounds__(256)
+equ_build_kernel(BlendImages b, long long pitch, const int32_t *__restrict__ flags, const int32_t *__restrict__ ids,
+                 int4 *__restrict__ A, float *__restrict__ X0, float *__restrict__ X1, float *__restrict__ B,
+                 int32_t *__restrict__ pix) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)b.n * b.m) return;
+  if (!flags[idx]) return;
+  const int i = (int)(idx / b.m), j = (int)(idx % b.m);
+  const int id = ids[idx];
+  // masked pixels are never on the crop frame, so the four neighbours exist
+  const long long nb[4] = {idx - b.m, idx + b.m, idx - 1, idx + 1};
+  const int di[4] = {-1, 1, 0, 0}, dj[4] = {0, 0, -1, 1};
+  int a[4];
+  bool out[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    out[k] = flags[nb[k]] == 0;
+    a[k] = out[k] ? 0 : ids[nb[k]];
+  }
+  A[id] = make_int4(a[0], a[1], a[2], a[3]);
+  pix[id - 1] = (int32_t)idx;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    float bv = pixel_gradient(b, i, j, ch);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (out[k]) bv += target_at(b, i + di[k], j + dj[k], ch);  // Dirichlet values folded into B
+    const float xv = target_at(b, i, j, ch);
+    B[ch * pitch + id] = bv;
+    X0[ch * pitch + id] = xv;
+    X1[ch * pitch + id] = xv;
+  }
+}
+
+// canvas[pix[i-1]] = u8(X[i])   (process.py:278)
+__global__ void __launch_bounds__(256)
+equ_paste_kernel(long long K, long long pitch, const float *__restrict__ x, const int32_t *__restrict__ pix,
+                 uint8_t *__restrict__ canvas) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  const long long p = pix[i];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) canvas[p * 3 + ch] = clip_byte(x[ch * pitch + i + 1]);
+}
+
+// ---------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------
+static int blocks_for(long long work, int threads) { return (int)ceil_div(work, threads); }
+
+EquSolver::EquSolver(int device, cudaStream_t stream, int block_size) : device_(device), stream_(stream) {
+  int count = 0;
+  CUDA_CHECK(cudaGetDeviceCount(&count));
+  FPIE_REQUIRE(device >= 0 && device < count, "fpie_b200: no such CUDA device");
+  DeviceGuard guard(device_);
+  cudaDeviceProp prop{};
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, device_));
+  FPIE_REQUIRE(prop.major >= 10, "fpie_b200 is built for sm_100a (Blackwell) only");
+  // the reference's -z flag (fpie/args.py block-size, default 1024); we accept
+  // any multiple of 32 up to 1024 and default to 256
+  if (block_size <= 0) block_size = 256;
+  block_ = std::min(1024, std::max(32, block_size / 32 * 32));
+  err_.resize(3);
+  flag_.resize(1);
+  CUDA_CHECK(cudaMallocHost(&host_err_, 3 * sizeof(double)));
+  CUDA_CHECK(cudaMallocHost(&host_flag_, sizeof(int)));
+}
+
+EquSolver::~EquSolver() {
+  cudaSetDevice(device_);
+  if (host_err_) cudaFreeHost(host_err_);
+  if (host_flag_) cudaFreeHost(host_flag_);
+}
+
+void EquSolver::require_ready() const { FPIE_REQUIRE(ready_, "EquSolver: step/state called before reset"); }
+
+void EquSolver::scan_ids(const int32_t *dev_mask, int64_t count, int32_t *dev_ids) {
+  const int nblocks = (int)ceil_div(count, SCAN_CHUNK);
+  block_sums_.resize(std::max(nblocks, 1));
+  scan_count_kernel<<<nblocks, SCAN_THREADS, 0, stream_>>>(dev_mask, count, block_sums_.ptr);
+  scan_block_sums_kernel<<<1, SCAN_THREADS, 0, stream_>>>(block_sums_.ptr, nblocks);
+  scan_write_kernel<<<nblocks, SCAN_THREADS, 0, stream_>>>(dev_mask, count, block_sums_.ptr, dev_ids);
+  CUDA_CHECK(cudaGetLastError());
+  stats_.launches += 3;
+}
+
+void EquSolver::partition(int n, int m, const int32_t *mask, int64_t mask_rs, int64_t mask_cs, int32_t *out_ids) {
+  FPIE_REQUIRE(n >= 1 && m >= 1 && mask && out_ids, "partition: bad arguments");
+  FPIE_REQUIRE(mask_cs == 1 && mask_rs >= m, "partition: mask rows must be contiguous (column stride 1)");
+  FPIE_REQUIRE((int64_t)n * m < (int64_t)1 << 31, "partition: more than 2^31 pixels");
+  DeviceGuard guard(device_);
+  const size_t count = (size_t)n * m;
+  istage_.resize(count);
+  ids_.resize(count);
+  CUDA_CHECK(cudaMemcpy2DAsync(istage_.ptr, (size_t)m * 4, mask, (size_t)mask_rs * 4, (size_t)m * 4, n,
+                               cudaMemcpyHostToDevice, stream_));
+  scan_ids(istage_.ptr, (int64_t)count, ids_.ptr);
+  CUDA_CHECK(cudaMemcpyAsync(out_ids, ids_.ptr, count * 4, cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+void EquSolver::allocate(int64_t N) {
+  N_ = N;
+  pitch_ = round_up(N, 32);
+  A_.resize((size_t)N);
+  for (auto &b : X_) b.resize((size_t)pitch_ * 3);
+  B_.resize((size_t)pitch_ * 3);
+  img_.resize((size_t)N * 3);
+  cur_ = 0;
+}
+
+void EquSolver::reset(int64_t N, const int32_t *A, const float *X, const float *B) {
+  FPIE_REQUIRE(N >= 1 && A && X && B, "EquSolver.reset: bad arguments");
+  FPIE_REQUIRE(N < ((int64_t)1 << 31), "EquSolver.reset: ids are int32");
+  DeviceGuard guard(device_);
+  ready_ = false;
+  fused_ = false;
+  allocate(N);
+  stage_.resize((size_t)N * 3);
+  CUDA_CHECK(cudaMemcpyAsync(A_.ptr, A, (size_t)N * 16, cudaMemcpyHostToDevice, stream_));
+  CUDA_CHECK(cudaMemsetAsync(flag_.ptr, 0, sizeof(int), stream_));
+  check_index_kernel<<<blocks_for(N, 256), 256, 0, stream_>>>(N, A_.ptr, flag_.ptr);
+  CUDA_CHECK(cudaMemcpyAsync(host_flag_, flag_.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaMemcpyAsync(stage_.ptr, X, (size_t)N * 12, cudaMemcpyHostToDevice, stream_));
+  rows3_to_planes_kernel<<<blocks_for(N, 256), 256, 0, stream_>>>(N, pitch_, stage_.ptr, X_[0].ptr, X_[1].ptr);
+  CUDA_CHECK(cudaMemcpyAsync(stage_.ptr, B, (size_t)N * 12, cudaMemcpyHostToDevice, stream_));
+  rows3_to_planes_kernel<<<blocks_for(N, 256), 256, 0, stream_>>>(N, pitch_, stage_.ptr, B_.ptr, nullptr);
+  CUDA_CHECK(cudaGetLastError());
+  stats_.launches += 3;
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  FPIE_REQUIRE(*host_flag_ == 0, "EquSolver.reset: A holds an index outside [0, N)");
+  stats_.unknowns = N - 1;
+  ready_ = true;
+}
+
+void EquSolver::reset_from_images(const uint8_t *src, int sh, int sw, const uint8_t *mask, int mh, int mw, int mc,
+                                  const uint8_t *tgt, int th, int tw, int h0, int w0, int h1, int w1, int grad_mode,
+                                  int64_t *out_n, int32_t *out_box4) {
+  DeviceGuard guard(device_);
+  ready_ = false;
+  BlendUpload up;
+  up.upload(stream_, src, sh, sw, mask, mh, mw, mc, tgt, th, tw, h0, w0, h1, w1, grad_mode);
+  const BlendImages &b = up.images();
+  const long long count = (long long)b.n * b.m;
+  FPIE_REQUIRE(count < (1ll << 31), "reset: crop has more than 2^31 pixels");
+  istage_.resize((size_t)count);
+  ids_.resize((size_t)count);
+  canvas_.resize((size_t)count * 3);
+  crop_flags_kernel<<<blocks_for(count, 256), 256, 0, stream_>>>(b, istage_.ptr, canvas_.ptr);
+  CUDA_CHECK(cudaGetLastError());
+  scan_ids(istage_.ptr, count, ids_.ptr);
+  int32_t last = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&last, ids_.ptr + (count - 1), 4, cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  const int64_t K = last;
+  allocate(K + 1);
+  pix_.resize((size_t)std::max<int64_t>(K, 1));
+  // row 0 of A / X / B is the zero constant (process.py:248-250)
+  CUDA_CHECK(cudaMemsetAsync(A_.ptr, 0, 16, stream_));
+  for (int ch = 0; ch < 3; ++ch) {
+    CUDA_CHECK(cudaMemsetAsync(X_[0].ptr + ch * pitch_, 0, 4, stream_));
+    CUDA_CHECK(cudaMemsetAsync(X_[1].ptr + ch * pitch_, 0, 4, stream_));
+    CUDA_CHECK(cudaMemsetAsync(B_.ptr + ch * pitch_, 0, 4, stream_));
+  }
+  equ_build_kernel<<<blocks_for(count, 256), 256, 0, stream_>>>(b, pitch_, istage_.ptr, ids_.ptr, A_.ptr, X_[0].ptr,
+                                                               X_[1].ptr, B_.ptr, pix_.ptr);
+  CUDA_CHECK(cudaGetLastError());
+  stats_.launches += 2;
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  crop_n_ = b.n;
+  crop_m_ = b.m;
+  fused_ = true;
+  stats_.unknowns = K;
+  ready_ = true;
+  if (out_n) *out_n = K + 1;
+  if (out_box4) {
+    out_box4[0] = b.h1 + b.x0;
+    out_box4[1] = b.h1 + b.x0 + b.n;
+    out_box4[2] = b.w1 + b.y0;
+    out_box4[3] = b.w1 + b.y0 + b.m;
+  }
+}
+
+void EquSolver::sweeps_async(int iters) {
+  require_ready();
+  FPIE_REQUIRE(iters >= 0, "step: negative iteration count");
+  DeviceGuard guard(device_);
+  for (int i = 0; i < iters; ++i) {
+    equ_sweep_kernel<<<blocks_for(N_, block_), block_, 0, stream_>>>(N_, pitch_, A_.ptr, B_.ptr, X_[cur_].ptr,
+                                                                    X_[cur_ ^ 1].ptr);
+    cur_ ^= 1;
+  }
+  stats_.launches += iters;
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void EquSolver::finish_async() {
+  require_ready();
+  DeviceGuard guard(device_);
+  CUDA_CHECK(cudaMemsetAsync(err_.ptr, 0, 3 * sizeof(double), stream_));
+  equ_residual_kernel<<<blocks_for(N_, 256), 256, 0, stream_>>>(N_, pitch_, A_.ptr, B_.ptr, X_[cur_].ptr, err_.ptr);
+  equ_to_u8_kernel<<<blocks_for(N_, 256), 256, 0, stream_>>>(N_, pitch_, X_[cur_].ptr, img_.ptr);
+  CUDA_CHECK(cudaGetLastError());
+  stats_.launches += 2;
+  CUDA_CHECK(cudaMemcpyAsync(host_err_, err_.ptr, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+}
+
+void EquSolver::sync() {
+  DeviceGuard guard(device_);
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+void EquSolver::fetch(uint8_t *out_img, float *out_err3) {
+  require_ready();
+  DeviceGuard guard(device_);
+  if (out_img) CUDA_CHECK(cudaMemcpyAsync(out_img, img_.ptr, (size_t)N_ * 3, cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  if (out_err3)
+    for (int c = 0; c < 3; ++c) out_err3[c] = (float)host_err_[c];
+}
+
+void EquSolver::step(int iters, uint8_t *out_img, float *out_err3) {
+  sweeps_async(iters);
+  finish_async();
+  fetch(out_img, out_err3);
+}
+
+void EquSolver::step_paste(int iters, uint8_t *out_crop, float *out_err3) {
+  require_ready();
+  FPIE_REQUIRE(fused_, "step_paste needs a solver reset with reset_from_images");
+  DeviceGuard guard(device_);
+  sweeps_async(iters);
+  CUDA_CHECK(cudaMemsetAsync(err_.ptr, 0, 3 * sizeof(double), stream_));
+  equ_residual_kernel<<<blocks_for(N_, 256), 256, 0, stream_>>>(N_, pitch_, A_.ptr, B_.ptr, X_[cur_].ptr, err_.ptr);
+  const int64_t K = N_ - 1;
+  if (K > 0)
+    equ_paste_kernel<<<blocks_for(K, 256), 256, 0, stream_>>>(K, pitch_, X_[cur_].ptr, pix_.ptr, canvas_.ptr);
+  CUDA_CHECK(cudaGetLastError());
+  stats_.launches += 2;
+  CUDA_CHECK(cudaMemcpyAsync(host_err_, err_.ptr, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  if (out_crop)
+    CUDA_CHECK(cudaMemcpyAsync(out_crop, canvas_.ptr, (size_t)crop_n_ * crop_m_ * 3, cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  if (out_err3)
+    for (int c = 0; c < 3; ++c) out_err3[c] = (float)host_err_[c];
+}
+
+void EquSolver::state(float *out) {
+  require_ready();
+  FPIE_REQUIRE(out, "state: null output");
+  DeviceGuard guard(device_);
+  stage_.resize((size_t)N_ * 3);
+  planes_to_rows3_kernel<<<blocks_for(N_, 256), 256, 0, stream_>>>(N_, pitch_, X_[cur_].ptr, stage_.ptr);
+  CUDA_CHECK(cudaGetLastError());
+  stats_.launches += 1;
+  CUDA_CHECK(cudaMemcpyAsync(out, stage_.ptr, (size_t)N_ * 12, cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+void EquSolver::system(int32_t *out_A, float *out_X, float *out_B) {
+  require_ready();
+  DeviceGuard guard(device_);
+  stage_.resize((size_t)N_ * 3);
+  if (out_A) CUDA_CHECK(cudaMemcpyAsync(out_A, A_.ptr, (size_t)N_ * 16, cudaMemcpyDeviceToHost, stream_));
+  if (out_X) {
+    planes_to_rows3_kernel<<<blocks_for(N_, 256), 256, 0, stream_>>>(N_, pitch_, X_[cur_].ptr, stage_.ptr);
+    CUDA_CHECK(cudaMemcpyAsync(out_X, stage_.ptr, (size_t)N_ * 12, cudaMemcpyDeviceToHost, stream_));
+  }
+  if (out_B) {
+    planes_to_rows3_kernel<<<blocks_for(N_, 256), 256, 0, stream_>>>(N_, pitch_, B_.ptr, stage_.ptr);
+    CUDA_CHECK(cudaMemcpyAsync(out_B, stage_.ptr, (size_t)N_ * 12, cudaMemcpyDeviceToHost, stream_));
+  }
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+}  // namespace fpie

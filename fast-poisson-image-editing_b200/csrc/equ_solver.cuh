@@ -1,0 +1,67 @@
+// EquSolver: index-mapped (gather) Jacobi on a compacted list of unknowns.
+#pragma once
+
+#include "common.cuh"
+
+namespace fpie {
+
+struct EquStats {
+  int64_t unknowns = 0;
+  int64_t launches = 0;
+};
+
+class EquSolver {
+ public:
+  EquSolver(int device, cudaStream_t stream, int block_size);
+  ~EquSolver();
+
+  void partition(int n, int m, const int32_t *mask, int64_t mask_rs, int64_t mask_cs, int32_t *out_ids);
+  void reset(int64_t N, const int32_t *A, const float *X, const float *B);
+  void reset_from_images(const uint8_t *src, int sh, int sw, const uint8_t *mask, int mh, int mw, int mc,
+                         const uint8_t *tgt, int th, int tw, int h0, int w0, int h1, int w1, int grad_mode,
+                         int64_t *out_n, int32_t *out_box4);
+  void sweeps_async(int iters);
+  void finish_async();
+  void sync();
+  void fetch(uint8_t *out_img, float *out_err3);
+  void step(int iters, uint8_t *out_img, float *out_err3);
+  void step_paste(int iters, uint8_t *out_crop, float *out_err3);
+  void state(float *out);
+  void system(int32_t *out_A, float *out_X, float *out_B);
+
+  const EquStats &stats() const { return stats_; }
+
+ private:
+  void require_ready() const;
+  void allocate(int64_t N);
+  // device-side inclusive scan of (mask > 0) over a contiguous device mask
+  void scan_ids(const int32_t *dev_mask, int64_t count, int32_t *dev_ids);
+
+  int device_;
+  cudaStream_t stream_;
+  int block_;
+  bool ready_ = false;
+  int64_t N_ = 0;      // rows including the constant row 0
+  int64_t pitch_ = 0;  // floats per channel plane of X / B
+  int cur_ = 0;
+  DeviceBuffer<int4> A_;
+  DeviceBuffer<float> X_[2];
+  DeviceBuffer<float> B_;
+  DeviceBuffer<float> stage_;
+  DeviceBuffer<int32_t> istage_;
+  DeviceBuffer<int32_t> ids_;
+  DeviceBuffer<uint32_t> block_sums_;
+  DeviceBuffer<uint8_t> img_;
+  DeviceBuffer<double> err_;
+  DeviceBuffer<int> flag_;
+  double *host_err_ = nullptr;
+  int *host_flag_ = nullptr;
+  // state of the fused Processor-level reset (scatter list + crop canvas)
+  bool fused_ = false;
+  int crop_n_ = 0, crop_m_ = 0;
+  DeviceBuffer<int32_t> pix_;     // [K] linear crop index of unknown i+1
+  DeviceBuffer<uint8_t> canvas_;  // [crop_n, crop_m, 3] target pixels of the crop
+  EquStats stats_;
+};
+
+}  // namespace fpie

@@ -1,0 +1,759 @@
+// GridSolver kernels + host driver (sm_100a).
+//
+// Replaces fpie/core/cuda/grid.cu (reference) with a different design:
+//   * planar, padded fp32 state (3 channel planes), 1-bit mask, quarter-scaled
+//     gradient planes -- the interleaved [n,m,3] layout exists only at the API;
+//   * true Jacobi (ping-pong buffers), bit-identical to fpie/np_solver.py:81-88;
+//   * temporally blocked sweeps: a CTA keeps a 128-wide register tile of one
+//     plane, runs k sweeps on it with a (k)-deep redundant halo and writes the
+//     interior back, so HBM is touched once per k sweeps;
+//   * tiles without masked pixels are never scheduled, fully masked tiles run
+//     a select-free instruction stream.
+
+#include <algorithm>
+#include <cstring>
+
+#include "grid_solver.cuh"
+#include "prep.cuh"
+#include "tma.cuh"
+
+namespace fpie {
+
+// ---------------------------------------------------------------------------
+// layout conversion
+// ---------------------------------------------------------------------------
+
+// int32 mask [n, m] (device, contiguous) -> 1 bit per pixel in the padded
+// geometry; the outer frame is forced to 0 (fpie/process.py:342-351 guarantees
+// it; base_solver.h:101-140 does not check).  One warp per output word.
+__global__ void pack_mask_kernel(PlaneGeom g, const int32_t *__restrict__ mask, uint32_t *__restrict__ bits,
+                                 unsigned long long *__restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long words = (long long)g.rows * g.wpitch;
+  if (warp >= words) return;
+  const int prow = (int)(warp / g.wpitch);
+  const int pcol = (int)(warp % g.wpitch) * 32 + lane;
+  const int r = prow - g.padr, c = pcol - g.padc;
+  bool on = false;
+  if (r > 0 && r < g.n - 1 && c > 0 && c < g.m - 1) on = mask[(long long)r * g.m + c] != 0;
+  const uint32_t word = __ballot_sync(0xffffffffu, on);
+  if (lane == 0) {
+    bits[warp] = word;
+    if (word) atomicAdd(count, (unsigned long long)__popc(word));
+  }
+}
+
+// interleaved fp32 [n, m, 3] -> three planes, scaled (1 for the state, 0.25
+// for the gradient); optionally mirrored into a second destination.
+__global__ void aos_to_planes_kernel(PlaneGeom g, const float *__restrict__ aos, float scale, float *__restrict__ dst0,
+                                     float *__restrict__ dst1) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long total = (long long)g.n * g.m;
+  if (idx >= total) return;
+  const int r = (int)(idx / g.m), c = (int)(idx % g.m);
+  const long long off = (long long)(r + g.padr) * g.pitch + (c + g.padc);
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const float v = aos[idx * 3 + ch] * scale;
+    dst0[ch * g.plane + off] = v;
+    if (dst1) dst1[ch * g.plane + off] = v;
+  }
+}
+
+__global__ void planes_to_aos_kernel(PlaneGeom g, const float *__restrict__ src, float *__restrict__ aos) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long total = (long long)g.n * g.m;
+  if (idx >= total) return;
+  const int r = (int)(idx / g.m), c = (int)(idx % g.m);
+  const long long off = (long long)(r + g.padr) * g.pitch + (c + g.padc);
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) aos[idx * 3 + ch] = src[ch * g.plane + off];
+}
+
+// ---------------------------------------------------------------------------
+// one Jacobi sweep per launch (fallback / cross-check path, variant 1)
+// thread = one 4-pixel group of one plane; groups without masked pixels exit
+// before touching the state (both ping-pong buffers hold the same constants).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+grid_sweep1_kernel(PlaneGeom g, int nplanes, const uint32_t *__restrict__ bits, const float *__restrict__ xin,
+                   float *__restrict__ xout, const float *__restrict__ hq) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long per_plane = (long long)g.n * g.groups;
+  if (idx >= per_plane * nplanes) return;
+  const int p = (int)(idx / per_plane);
+  const long long q = idx % per_plane;
+  const int r = (int)(q / g.groups), grp = (int)(q % g.groups);
+  const int pc = g.padc + 4 * grp;
+  const uint32_t nib = (bits[(long long)(r + g.padr) * g.wpitch + (pc >> 5)] >> (pc & 31)) & 0xFu;
+  if (!nib) return;
+  const long long off = (long long)p * g.plane + (long long)(r + g.padr) * g.pitch + pc;
+  const float4 c = ld4(xin + off), u = ld4(xin + off - g.pitch), d = ld4(xin + off + g.pitch), h = ld4(hq + off);
+  const float lf = xin[off - 1], rt = xin[off + 4];
+  float4 o;
+  o.x = (nib & 1u) ? jacobi_q(h.x, u.x, d.x, lf, c.y) : c.x;
+  o.y = (nib & 2u) ? jacobi_q(h.y, u.y, d.y, c.x, c.z) : c.y;
+  o.z = (nib & 4u) ? jacobi_q(h.z, u.z, d.z, c.y, c.w) : c.z;
+  o.w = (nib & 8u) ? jacobi_q(h.w, u.w, d.w, c.z, rt) : c.w;
+  st4(xout + off, o);
+}
+
+// ---------------------------------------------------------------------------
+// temporally blocked sweeps: nsweeps (<= K) Jacobi sweeps per pass over HBM.
+//
+// Tile = (R * NW) rows x 128 cols of one plane, held in registers: thread
+// (warp w, lane l) owns rows [w*R, (w+1)*R) x cols [4l, 4l+4).  Per sweep a
+// thread needs the row above / below its strip (other warps: exchanged through
+// a 2-deep shared-memory mailbox, one __syncthreads per sweep) and the
+// columns left / right of it (other lanes: warp shuffles).  Values within s
+// pixels of the tile edge are wrong after s sweeps; the tile origin is chosen
+// so that only the inner (TH-2K) x (128-2HK) region is stored.
+// ---------------------------------------------------------------------------
+template <int R, bool MIXED>
+__device__ __forceinline__ void tile_sweep(float4 (&x)[R], const float4 (&h)[R], const uint32_t (&mb)[(R + 7) / 8],
+                                           float4 up, float4 dn) {
+  float4 prev = up;
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const float4 cur = x[i];
+    const float4 nxt = (i + 1 < R) ? x[i + 1] : dn;
+    const float lf = __shfl_up_sync(0xffffffffu, cur.w, 1);
+    const float rt = __shfl_down_sync(0xffffffffu, cur.x, 1);
+    float4 o;
+    o.x = jacobi_q(h[i].x, prev.x, nxt.x, lf, cur.y);
+    o.y = jacobi_q(h[i].y, prev.y, nxt.y, cur.x, cur.z);
+    o.z = jacobi_q(h[i].z, prev.z, nxt.z, cur.y, cur.w);
+    o.w = jacobi_q(h[i].w, prev.w, nxt.w, cur.z, rt);
+    if (MIXED) {
+      const uint32_t nib = mb[i / 8] >> ((i % 8) * 4);
+      o.x = (nib & 1u) ? o.x : cur.x;
+      o.y = (nib & 2u) ? o.y : cur.y;
+      o.z = (nib & 4u) ? o.z : cur.z;
+      o.w = (nib & 8u) ? o.w : cur.w;
+    }
+    x[i] = o;
+    prev = cur;
+  }
+}
+
+// sweeps + store of one register tile (shared by the direct-load and the
+// TMA-pipelined kernels).  `parity` carries the mailbox double-buffer phase
+// across tiles: there is exactly one __syncthreads per sweep.
+template <int R, int NW>
+__device__ __forceinline__ void tile_run(float4 (&x)[R], const float4 (&h)[R], uint32_t (&mb)[(R + 7) / 8], bool full,
+                                         float4 (*mailbox)[2][NW][32], int &parity, int nsweeps, int halo_y,
+                                         int halo_x, float *__restrict__ out, int pitch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  constexpr int TH = R * NW;
+  for (int s = 0; s < nsweeps; ++s) {
+    mailbox[parity][0][w][lane] = x[0];
+    mailbox[parity][1][w][lane] = x[R - 1];
+    __syncthreads();
+    const float4 up = (w > 0) ? mailbox[parity][1][w - 1][lane] : x[0];
+    const float4 dn = (w + 1 < NW) ? mailbox[parity][0][w + 1][lane] : x[R - 1];
+    parity ^= 1;
+    if (full)
+      tile_sweep<R, false>(x, h, mb, up, dn);
+    else
+      tile_sweep<R, true>(x, h, mb, up, dn);
+  }
+  // store the inner region; groups without masked pixels keep their constants
+  const bool lane_in = (4 * lane >= halo_x) && (4 * lane < TILE_W - halo_x);
+  if (lane_in) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const int tr = w * R + i;
+      const uint32_t nib = (mb[i / 8] >> ((i % 8) * 4)) & 0xFu;
+      if (tr >= halo_y && tr < TH - halo_y && nib) st4(out + (long long)i * pitch, x[i]);
+    }
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void load_mask_bits(uint32_t (&mb)[(R + 7) / 8], bool full,
+                                               const uint32_t *__restrict__ bits, int wpitch, int prow0, int pcol) {
+#pragma unroll
+  for (int i = 0; i < (R + 7) / 8; ++i) mb[i] = full ? 0xffffffffu : 0u;
+  if (!full) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const uint32_t word = bits[(long long)(prow0 + i) * wpitch + (pcol >> 5)];
+      mb[i / 8] |= ((word >> (pcol & 31)) & 0xFu) << ((i % 8) * 4);
+    }
+  }
+}
+
+// direct-load variant: registers are filled straight from global memory
+template <int R, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+grid_sweepk_kernel(PlaneGeom g, const uint32_t *__restrict__ bits, const float *__restrict__ xin,
+                   float *__restrict__ xout, const float *__restrict__ hq, const int4 *__restrict__ tiles, int ntiles,
+                   int nsweeps, int halo_y, int halo_x) {
+  __shared__ float4 mailbox[2][2][NW][32];  // [sweep parity][0 = top row, 1 = bottom row][warp][lane]
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int parity = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int4 td = tiles[t];  // x = plane row of tile origin, y = plane col, z = plane, w = flags (1 = fully masked)
+    const int prow0 = td.x + w * R;
+    const int pcol = td.y + 4 * lane;
+    const long long base = (long long)td.z * g.plane + (long long)prow0 * g.pitch + pcol;
+    const bool full = (td.w & 1) != 0;
+    float4 x[R], h[R];
+    uint32_t mb[(R + 7) / 8];
+#pragma unroll
+    for (int i = 0; i < R; ++i) x[i] = ld4(xin + base + (long long)i * g.pitch);
+#pragma unroll
+    for (int i = 0; i < R; ++i) h[i] = ld4(hq + base + (long long)i * g.pitch);
+    load_mask_bits<R>(mb, full, bits, g.wpitch, prow0, pcol);
+    tile_run<R, NW>(x, h, mb, full, mailbox, parity, nsweeps, halo_y, halo_x, xout + base, g.pitch);
+  }
+}
+
+// TMA-pipelined variant: while the CTA sweeps the tile it holds in registers,
+// the TMA engine streams the next tile (state + quarter-gradient, 2 x TH x 512 B)
+// into shared memory; one elected thread arms an mbarrier with the byte count
+// and issues two cp.async.bulk.tensor loads.  smem -> registers is a
+// conflict-free 128-bit copy (each warp reads one 512-byte row).
+template <int R, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+grid_sweepk_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h,
+                       PlaneGeom g, const uint32_t *__restrict__ bits, float *__restrict__ xout,
+                       const int4 *__restrict__ tiles, int ntiles, int nsweeps, int halo_y, int halo_x) {
+  constexpr int TH = R * NW;
+  constexpr uint32_t TILE_BYTES = TH * TILE_W * 4;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  float *sx = reinterpret_cast<float *>(smem_raw);
+  float *sh = sx + TH * TILE_W;
+  float4(*mailbox)[2][NW][32] = reinterpret_cast<float4(*)[2][NW][32]>(sh + TH * TILE_W);
+  __shared__ uint64_t bar;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  int t = blockIdx.x;
+  if (threadIdx.x == 0 && t < ntiles) {
+    const int4 td = tiles[t];
+    mbar_expect_tx(&bar, 2 * TILE_BYTES);
+    tma_load_3d(sx, &tm_x, td.y, td.x, td.z, &bar);
+    tma_load_3d(sh, &tm_h, td.y, td.x, td.z, &bar);
+  }
+  int parity = 0;
+  uint32_t phase = 0;
+  for (; t < ntiles; t += gridDim.x) {
+    const int4 td = tiles[t];
+    const int prow0 = td.x + w * R;
+    const int pcol = td.y + 4 * lane;
+    const long long base = (long long)td.z * g.plane + (long long)prow0 * g.pitch + pcol;
+    const bool full = (td.w & 1) != 0;
+    float4 x[R], h[R];
+    uint32_t mb[(R + 7) / 8];
+    load_mask_bits<R>(mb, full, bits, g.wpitch, prow0, pcol);
+
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    const int soff = (w * R) * TILE_W + 4 * lane;
+#pragma unroll
+    for (int i = 0; i < R; ++i) x[i] = ld4(sx + soff + i * TILE_W);
+#pragma unroll
+    for (int i = 0; i < R; ++i) h[i] = ld4(sh + soff + i * TILE_W);
+    __syncthreads();  // every thread has drained the staging buffers
+    const int tn = t + gridDim.x;
+    if (threadIdx.x == 0 && tn < ntiles) {
+      const int4 nd = tiles[tn];
+      mbar_expect_tx(&bar, 2 * TILE_BYTES);
+      tma_load_3d(sx, &tm_x, nd.y, nd.x, nd.z, &bar);
+      tma_load_3d(sh, &tm_h, nd.y, nd.x, nd.z, &bar);
+    }
+    tile_run<R, NW>(x, h, mb, full, mailbox, parity, nsweeps, halo_y, halo_x, xout + base, g.pitch);
+  }
+}
+
+// Classify the tile grid: flag bit0 = some masked pixel in the stored (inner)
+// region, bit1 = every pixel of the whole tile masked.  One CTA per tile.
+__global__ void classify_tiles_kernel(PlaneGeom g, const uint32_t *__restrict__ bits, int tiles_x, int tile_h,
+                                      int step_y, int step_x, int halo_y, int halo_x, uint32_t *__restrict__ flags) {
+  const int tile = blockIdx.x;
+  const int ty = tile / tiles_x, tx = tile % tiles_x;
+  const int prow0 = g.padr + ty * step_y - halo_y;
+  const int pcol0 = g.padc + tx * step_x - halo_x;
+  int any_inner = 0, all_full = 1;
+  for (int q = threadIdx.x; q < tile_h * 32; q += blockDim.x) {
+    const int tr = q >> 5, l = q & 31;
+    const int pc = pcol0 + 4 * l;
+    const uint32_t nib = (bits[(long long)(prow0 + tr) * g.wpitch + (pc >> 5)] >> (pc & 31)) & 0xFu;
+    if (nib != 0xFu) all_full = 0;
+    if (nib && tr >= halo_y && tr < tile_h - halo_y && 4 * l >= halo_x && 4 * l < TILE_W - halo_x) any_inner = 1;
+  }
+  any_inner = __syncthreads_or(any_inner);
+  all_full = __syncthreads_and(all_full);
+  if (threadIdx.x == 0) flags[tile] = (any_inner ? 1u : 0u) | (all_full ? 2u : 0u);
+}
+
+// ---------------------------------------------------------------------------
+// epilogue: residual (fpie/np_solver.py:90-96) and uint8 image (grid.cu:115-131)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float resid_term(float t, float hq, float up, float dn, float lf, float rt) {
+  float v = __fsub_rn(__fmul_rn(4.0f, t), __fmul_rn(4.0f, hq));  // 4t - g
+  v = __fsub_rn(v, up);
+  v = __fsub_rn(v, dn);
+  v = __fsub_rn(v, lf);
+  v = __fsub_rn(v, rt);
+  return fabsf(v);
+}
+
+// grid: (blocks over rows x groups, plane).  err[plane % 3] accumulates in double.
+__global__ void __launch_bounds__(256)
+grid_residual_kernel(PlaneGeom g, int row_lo, int row_hi, const uint32_t *__restrict__ bits,
+                     const float *__restrict__ x, const float *__restrict__ hq, double *__restrict__ err) {
+  const int p = blockIdx.y;
+  const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long per_plane = (long long)(row_hi - row_lo) * g.groups;
+  float acc = 0.f;
+  if (q < per_plane) {
+    const int r = row_lo + (int)(q / g.groups), grp = (int)(q % g.groups);
+    const int pc = g.padc + 4 * grp;
+    const uint32_t nib = (bits[(long long)(r + g.padr) * g.wpitch + (pc >> 5)] >> (pc & 31)) & 0xFu;
+    if (nib) {
+      const long long off = (long long)p * g.plane + (long long)(r + g.padr) * g.pitch + pc;
+      const float4 c = ld4(x + off), u = ld4(x + off - g.pitch), d = ld4(x + off + g.pitch), h = ld4(hq + off);
+      const float lf = x[off - 1], rt = x[off + 4];
+      if (nib & 1u) acc += resid_term(c.x, h.x, u.x, d.x, lf, c.y);
+      if (nib & 2u) acc += resid_term(c.y, h.y, u.y, d.y, c.x, c.z);
+      if (nib & 4u) acc += resid_term(c.z, h.z, u.z, d.z, c.y, c.w);
+      if (nib & 8u) acc += resid_term(c.w, h.w, u.w, d.w, c.z, rt);
+    }
+  }
+  // warp shuffle reduction, then one partial per warp through shared memory
+  double v = (double)acc;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  __shared__ double partial[8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) partial[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = (lane < (blockDim.x >> 5)) ? partial[lane] : 0.0;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0 && v != 0.0) atomicAdd(&err[p % 3], v);
+  }
+}
+
+__device__ __forceinline__ uint32_t clip_u8(float v) { return __float2uint_rz(fminf(fmaxf(v, 0.f), 255.f)); }
+
+// thread = 4 pixels x 3 channels -> 12 interleaved bytes of img[n, m, 3]
+__global__ void __launch_bounds__(256)
+grid_to_u8_kernel(PlaneGeom g, const float *__restrict__ x, uint8_t *__restrict__ img) {
+  const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (q >= (long long)g.n * g.groups) return;
+  const int r = (int)(q / g.groups), grp = (int)(q % g.groups);
+  const long long off = (long long)(r + g.padr) * g.pitch + g.padc + 4 * grp;
+  const float4 a = ld4(x + off), b = ld4(x + g.plane + off), c = ld4(x + 2 * g.plane + off);
+  const uint32_t a0 = clip_u8(a.x), a1 = clip_u8(a.y), a2 = clip_u8(a.z), a3 = clip_u8(a.w);
+  const uint32_t b0 = clip_u8(b.x), b1 = clip_u8(b.y), b2 = clip_u8(b.z), b3 = clip_u8(b.w);
+  const uint32_t c0 = clip_u8(c.x), c1 = clip_u8(c.y), c2 = clip_u8(c.z), c3 = clip_u8(c.w);
+  const long long o = ((long long)r * g.m + 4 * grp) * 3;
+  const int valid = min(4, g.m - 4 * grp);
+  if (valid == 4 && (o & 3) == 0) {
+    uint32_t *dst = reinterpret_cast<uint32_t *>(img + o);
+    dst[0] = a0 | (b0 << 8) | (c0 << 16) | (a1 << 24);
+    dst[1] = b1 | (c1 << 8) | (a2 << 16) | (b2 << 24);
+    dst[2] = c2 | (a3 << 8) | (b3 << 16) | (c3 << 24);
+  } else {
+    const uint32_t px[4][3] = {{a0, b0, c0}, {a1, b1, c1}, {a2, b2, c2}, {a3, b3, c3}};
+    for (int k = 0; k < valid; ++k)
+      for (int ch = 0; ch < 3; ++ch) img[o + k * 3 + ch] = (uint8_t)px[k][ch];
+  }
+}
+
+// Fused Processor-level reset (fpie/process.py:338-378): one warp builds 32
+// consecutive plane columns of one crop row -- mask word by ballot, state from
+// the target crop, quarter-scaled mixed gradient on masked pixels.
+__global__ void __launch_bounds__(256)
+grid_build_kernel(PlaneGeom g, BlendImages b, uint32_t *__restrict__ bits, float *__restrict__ x0,
+                  float *__restrict__ x1, float *__restrict__ hq, unsigned long long *__restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (warp >= (long long)g.n * g.wpitch) return;
+  const int r = (int)(warp / g.wpitch);
+  const int pcol = (int)(warp % g.wpitch) * 32 + lane;
+  const int c = pcol - g.padc;
+  const bool inside = c >= 0 && c < g.m;
+  const bool on = inside && canonical_mask_at(b, b.x0 + r, b.y0 + c);
+  const uint32_t word = __ballot_sync(0xffffffffu, on);
+  const long long prow = r + g.padr;
+  if (lane == 0) {
+    bits[prow * g.wpitch + (pcol >> 5)] = word;
+    if (word) atomicAdd(count, (unsigned long long)__popc(word));
+  }
+  if (!inside) return;
+  const long long off = prow * g.pitch + pcol;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const float t = target_at(b, r, c, ch);
+    x0[ch * g.plane + off] = t;
+    x1[ch * g.plane + off] = t;
+    hq[ch * g.plane + off] = on ? 0.25f * pixel_gradient(b, r, c, ch) : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------
+static int blocks_for(long long work, int threads) { return (int)ceil_div(work, threads); }
+
+GridSolver::GridSolver(int device, cudaStream_t stream, int block_k, int variant)
+    : device_(device), stream_(stream), variant_(variant) {
+  int count = 0;
+  CUDA_CHECK(cudaGetDeviceCount(&count));
+  FPIE_REQUIRE(device >= 0 && device < count, "fpie_b200: no such CUDA device");
+  DeviceGuard guard(device_);
+  cudaDeviceProp prop{};
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, device_));
+  FPIE_REQUIRE(prop.major >= 10, "fpie_b200 is built for sm_100a (Blackwell) only");
+  sm_count_ = prop.multiProcessorCount;
+  if (block_k <= 0) block_k = 8;
+  FPIE_REQUIRE(block_k <= MAX_BLOCK_K, "block_k must be in 1..16");
+  block_k_ = block_k;
+  halo_x_ = (int)round_up(block_k_, 4);
+  shape_ = shape_for(variant_);
+  FPIE_REQUIRE(shape_.tile_h() > 2 * block_k_, "block_k too deep for the tile height");
+  err_.resize(4);
+  CUDA_CHECK(cudaMallocHost(&host_err_, 4 * sizeof(double)));
+}
+
+GridSolver::~GridSolver() {
+  cudaSetDevice(device_);
+  if (host_err_) cudaFreeHost(host_err_);
+}
+
+void GridSolver::require_ready() const { FPIE_REQUIRE(ready_, "GridSolver: step/state called before reset"); }
+
+void GridSolver::layout(int n, int m) {
+  FPIE_REQUIRE(n >= 1 && m >= 1, "GridSolver.reset: empty grid");
+  const int step_x = TILE_W - 2 * halo_x_, step_y = shape_.tile_h() - 2 * block_k_;
+  const int tiles_x = (int)ceil_div(m, step_x), tiles_y = (int)ceil_div(n, step_y);
+  PlaneGeom g{};
+  g.n = n;
+  g.m = m;
+  g.padr = PAD_ROWS;
+  g.padc = PAD_COLS;
+  g.pitch = (int)round_up(g.padc + (long long)tiles_x * step_x + halo_x_ + 4, 32);
+  g.rows = g.padr + tiles_y * step_y + block_k_ + 1;
+  g.wpitch = g.pitch / 32;
+  g.groups = (int)ceil_div(m, 4);
+  g.plane = (long long)g.rows * g.pitch;
+  geom_ = g;
+  win_lo_ = 0;
+  win_hi_ = n;
+}
+
+void GridSolver::reset(int n, int m, const int32_t *mask, int64_t mask_rs, int64_t mask_cs, const float *tgt,
+                       const float *grad) {
+  FPIE_REQUIRE(mask && tgt && grad, "GridSolver.reset: null input");
+  FPIE_REQUIRE(mask_cs == 1 && mask_rs >= m, "GridSolver.reset: mask rows must be contiguous (column stride 1)");
+  DeviceGuard guard(device_);
+  ready_ = false;
+  layout(n, m);
+  const PlaneGeom &g = geom_;
+  const size_t pixels = (size_t)n * m;
+  for (auto &b : x_) b.resize((size_t)g.plane * 3);
+  hq_.resize((size_t)g.plane * 3);
+  bits_.resize((size_t)g.rows * g.wpitch);
+  stage_.resize(pixels * 3);
+  mask_stage_.resize(pixels);
+  img_.resize(pixels * 3);
+
+  CUDA_CHECK(cudaMemsetAsync(x_[0].ptr, 0, x_[0].bytes(), stream_));
+  CUDA_CHECK(cudaMemsetAsync(x_[1].ptr, 0, x_[1].bytes(), stream_));
+  CUDA_CHECK(cudaMemsetAsync(hq_.ptr, 0, hq_.bytes(), stream_));
+  CUDA_CHECK(cudaMemsetAsync(err_.ptr, 0, err_.bytes(), stream_));
+
+  CUDA_CHECK(cudaMemcpy2DAsync(mask_stage_.ptr, (size_t)m * 4, mask, (size_t)mask_rs * 4, (size_t)m * 4, n,
+                               cudaMemcpyHostToDevice, stream_));
+  {
+    const long long warps = (long long)g.rows * g.wpitch;
+    pack_mask_kernel<<<blocks_for(warps * 32, 256), 256, 0, stream_>>>(
+        g, mask_stage_.ptr, bits_.ptr, reinterpret_cast<unsigned long long *>(err_.ptr + 3));
+    CUDA_CHECK(cudaGetLastError());
+  }
+  CUDA_CHECK(cudaMemcpyAsync(stage_.ptr, tgt, pixels * 12, cudaMemcpyHostToDevice, stream_));
+  aos_to_planes_kernel<<<blocks_for(pixels, 256), 256, 0, stream_>>>(g, stage_.ptr, 1.0f, x_[0].ptr, x_[1].ptr);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaMemcpyAsync(stage_.ptr, grad, pixels * 12, cudaMemcpyHostToDevice, stream_));
+  aos_to_planes_kernel<<<blocks_for(pixels, 256), 256, 0, stream_>>>(g, stage_.ptr, 0.25f, hq_.ptr, nullptr);
+  CUDA_CHECK(cudaGetLastError());
+  stats_.launches += 3;
+  after_state_loaded();
+}
+
+void GridSolver::reset_from_images(const uint8_t *src, int sh, int sw, const uint8_t *mask, int mh, int mw, int mc,
+                                   const uint8_t *tgt, int th, int tw, int h0, int w0, int h1, int w1, int grad_mode,
+                                   int64_t *out_n, int32_t *out_box4) {
+  DeviceGuard guard(device_);
+  ready_ = false;
+  BlendUpload up;
+  up.upload(stream_, src, sh, sw, mask, mh, mw, mc, tgt, th, tw, h0, w0, h1, w1, grad_mode);
+  const BlendImages &b = up.images();
+  layout(b.n, b.m);
+  const PlaneGeom &g = geom_;
+  for (auto &buf : x_) buf.resize((size_t)g.plane * 3);
+  hq_.resize((size_t)g.plane * 3);
+  bits_.resize((size_t)g.rows * g.wpitch);
+  img_.resize((size_t)g.n * g.m * 3);
+  CUDA_CHECK(cudaMemsetAsync(x_[0].ptr, 0, x_[0].bytes(), stream_));
+  CUDA_CHECK(cudaMemsetAsync(x_[1].ptr, 0, x_[1].bytes(), stream_));
+  CUDA_CHECK(cudaMemsetAsync(hq_.ptr, 0, hq_.bytes(), stream_));
+  CUDA_CHECK(cudaMemsetAsync(bits_.ptr, 0, bits_.bytes(), stream_));
+  CUDA_CHECK(cudaMemsetAsync(err_.ptr, 0, err_.bytes(), stream_));
+  const long long warps = (long long)g.n * g.wpitch;
+  grid_build_kernel<<<blocks_for(warps * 32, 256), 256, 0, stream_>>>(
+      g, b, bits_.ptr, x_[0].ptr, x_[1].ptr, hq_.ptr, reinterpret_cast<unsigned long long *>(err_.ptr + 3));
+  CUDA_CHECK(cudaGetLastError());
+  stats_.launches += 2;
+  after_state_loaded();
+  if (out_n) *out_n = (int64_t)g.n * g.m;
+  if (out_box4) {
+    out_box4[0] = b.h1 + b.x0;
+    out_box4[1] = b.h1 + b.x0 + b.n;
+    out_box4[2] = b.w1 + b.y0;
+    out_box4[3] = b.w1 + b.y0 + b.m;
+  }
+}
+
+void GridSolver::after_state_loaded() {
+  make_tensor_maps();
+  // unknown count (stored as a 64-bit integer in err_[3])
+  CUDA_CHECK(cudaMemcpyAsync(host_err_ + 3, err_.ptr + 3, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  build_tiles();
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  unsigned long long cnt;
+  memcpy(&cnt, host_err_ + 3, sizeof(cnt));
+  stats_.unknowns = (int64_t)cnt;
+  cur_ = 0;
+  ready_ = true;
+}
+
+void GridSolver::build_tiles() {
+  const PlaneGeom &g = geom_;
+  const int step_x = TILE_W - 2 * halo_x_, step_y = shape_.tile_h() - 2 * block_k_;
+  const int tiles_x = (int)ceil_div(g.m, step_x), tiles_y = (int)ceil_div(g.n, step_y);
+  const int ntiles = tiles_x * tiles_y;
+  tile_flags_.resize(ntiles);
+  classify_tiles_kernel<<<ntiles, 256, 0, stream_>>>(g, bits_.ptr, tiles_x, shape_.tile_h(), step_y, step_x, block_k_,
+                                                     halo_x_, tile_flags_.ptr);
+  CUDA_CHECK(cudaGetLastError());
+  stats_.launches += 1;
+  std::vector<uint32_t> flags(ntiles);
+  CUDA_CHECK(cudaMemcpyAsync(flags.data(), tile_flags_.ptr, ntiles * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  std::vector<int4> list;
+  list.reserve((size_t)ntiles * 3);
+  int64_t active = 0;
+  for (int t = 0; t < ntiles; ++t) {
+    if (!(flags[t] & 1u)) continue;
+    ++active;
+    const int ty = t / tiles_x, tx = t % tiles_x;
+    for (int ch = 0; ch < 3; ++ch)
+      list.push_back(make_int4(g.padr + ty * step_y - block_k_, g.padc + tx * step_x - halo_x_, ch,
+                               (flags[t] & 2u) ? 1 : 0));
+  }
+  stats_.active_tiles = active;
+  stats_.total_tiles = ntiles;
+  n_tile_entries_ = (int)list.size();
+  tiles_.resize(std::max<size_t>(list.size(), 1));
+  if (!list.empty())
+    CUDA_CHECK(cudaMemcpyAsync(tiles_.ptr, list.data(), list.size() * sizeof(int4), cudaMemcpyHostToDevice, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+namespace {
+
+struct SweepArgs {
+  int grid;
+  cudaStream_t stream;
+  PlaneGeom g;
+  const uint32_t *bits;
+  const float *xin;
+  float *xout;
+  const float *hq;
+  const CUtensorMap *tm_x;
+  const CUtensorMap *tm_h;
+  const int4 *tiles;
+  int ntiles, nsweeps, halo_y, halo_x;
+};
+
+template <int R, int NW>
+void launch_direct(const SweepArgs &a) {
+  grid_sweepk_kernel<R, NW><<<a.grid, NW * 32, 0, a.stream>>>(a.g, a.bits, a.xin, a.xout, a.hq, a.tiles, a.ntiles,
+                                                              a.nsweeps, a.halo_y, a.halo_x);
+}
+
+template <int R, int NW>
+constexpr size_t tma_smem_bytes() {
+  return (size_t)2 * R * NW * TILE_W * 4 + sizeof(float4) * 2 * 2 * NW * 32;
+}
+
+template <int R, int NW>
+void launch_tma(const SweepArgs &a) {
+  auto kernel = grid_sweepk_tma_kernel<R, NW>;
+  constexpr size_t smem = tma_smem_bytes<R, NW>();
+  static int configured_device = -1;  // the attribute is per function and per device
+  int dev = 0;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  if (configured_device != dev) {
+    CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured_device = dev;
+  }
+  kernel<<<a.grid, NW * 32, smem, a.stream>>>(*a.tm_x, *a.tm_h, a.g, a.bits, a.xout, a.tiles, a.ntiles, a.nsweeps,
+                                              a.halo_y, a.halo_x);
+}
+
+}  // namespace
+
+// kernel variants (fpie_b200_grid_create `variant`):
+//   0  TMA-pipelined, 16 rows/thread x 12 warps (tile 192 x 128)   [default]
+//   1  one sweep per launch
+//   2  direct loads, 16 x 8      3  direct loads, 8 x 16      4  direct loads, 16 x 12
+//   5  TMA-pipelined, 16 x 8     6  TMA-pipelined, 8 x 16
+TileShape GridSolver::shape_for(int variant) {
+  switch (variant) {
+    case 0: case 1: case 4: return {16, 12};
+    case 2: case 5: return {16, 8};
+    case 3: case 6: return {8, 16};
+    default: throw Error("fpie_b200: unknown grid kernel variant");
+  }
+}
+
+void GridSolver::make_tensor_maps() {
+  const PlaneGeom &g = geom_;
+  for (int i = 0; i < 2; ++i)
+    tm_x_[i] = make_plane_tensor_map(x_[i].ptr, g.pitch, g.rows, 3, g.plane, TILE_W, shape_.tile_h());
+  tm_h_ = make_plane_tensor_map(hq_.ptr, g.pitch, g.rows, 3, g.plane, TILE_W, shape_.tile_h());
+}
+
+void GridSolver::sweeps_async(int iters) {
+  require_ready();
+  FPIE_REQUIRE(iters >= 0, "step: negative iteration count");
+  DeviceGuard guard(device_);
+  const PlaneGeom &g = geom_;
+  if (stats_.unknowns == 0 || iters == 0) return;
+  if (variant_ == 1) {
+    const long long work = (long long)g.n * g.groups * 3;
+    for (int i = 0; i < iters; ++i) {
+      grid_sweep1_kernel<<<blocks_for(work, 256), 256, 0, stream_>>>(g, 3, bits_.ptr, x_[cur_].ptr, x_[cur_ ^ 1].ptr,
+                                                                     hq_.ptr);
+      cur_ ^= 1;
+    }
+    stats_.launches += iters;
+    CUDA_CHECK(cudaGetLastError());
+    return;
+  }
+  SweepArgs a{};
+  a.grid = std::min(n_tile_entries_, sm_count_);
+  a.stream = stream_;
+  a.g = g;
+  a.bits = bits_.ptr;
+  a.hq = hq_.ptr;
+  a.tm_h = &tm_h_;
+  a.tiles = tiles_.ptr;
+  a.ntiles = n_tile_entries_;
+  a.halo_y = block_k_;
+  a.halo_x = halo_x_;
+  int left = iters;
+  while (left > 0) {
+    a.nsweeps = std::min(left, block_k_);
+    a.xin = x_[cur_].ptr;
+    a.xout = x_[cur_ ^ 1].ptr;
+    a.tm_x = &tm_x_[cur_];
+    switch (variant_) {
+      case 0: launch_tma<16, 12>(a); break;
+      case 2: launch_direct<16, 8>(a); break;
+      case 3: launch_direct<8, 16>(a); break;
+      case 4: launch_direct<16, 12>(a); break;
+      case 5: launch_tma<16, 8>(a); break;
+      case 6: launch_tma<8, 16>(a); break;
+      default: throw Error("fpie_b200: unknown grid kernel variant");
+    }
+    cur_ ^= 1;
+    left -= a.nsweeps;
+    stats_.launches += 1;
+  }
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void GridSolver::finish_async() {
+  require_ready();
+  DeviceGuard guard(device_);
+  const PlaneGeom &g = geom_;
+  CUDA_CHECK(cudaMemsetAsync(err_.ptr, 0, 3 * sizeof(double), stream_));
+  const long long work = (long long)(win_hi_ - win_lo_) * g.groups;
+  if (work > 0 && stats_.unknowns > 0) {
+    dim3 grid(blocks_for(work, 256), 3);
+    grid_residual_kernel<<<grid, 256, 0, stream_>>>(g, win_lo_, win_hi_, bits_.ptr, x_[cur_].ptr, hq_.ptr, err_.ptr);
+    CUDA_CHECK(cudaGetLastError());
+    stats_.launches += 1;
+  }
+  grid_to_u8_kernel<<<blocks_for((long long)g.n * g.groups, 256), 256, 0, stream_>>>(g, x_[cur_].ptr, img_.ptr);
+  CUDA_CHECK(cudaGetLastError());
+  stats_.launches += 1;
+  CUDA_CHECK(cudaMemcpyAsync(host_err_, err_.ptr, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+}
+
+void GridSolver::sync() {
+  DeviceGuard guard(device_);
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+void GridSolver::fetch(uint8_t *out_img, float *out_err3) {
+  require_ready();
+  DeviceGuard guard(device_);
+  if (out_img)
+    CUDA_CHECK(cudaMemcpyAsync(out_img, img_.ptr, (size_t)geom_.n * geom_.m * 3, cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  if (out_err3)
+    for (int c = 0; c < 3; ++c) out_err3[c] = (float)host_err_[c];
+}
+
+void GridSolver::step(int iters, uint8_t *out_img, float *out_err3) {
+  sweeps_async(iters);
+  finish_async();
+  fetch(out_img, out_err3);
+}
+
+void GridSolver::state(float *out) {
+  require_ready();
+  FPIE_REQUIRE(out, "state: null output");
+  DeviceGuard guard(device_);
+  const size_t pixels = (size_t)geom_.n * geom_.m;
+  stage_.resize(pixels * 3);
+  planes_to_aos_kernel<<<blocks_for(pixels, 256), 256, 0, stream_>>>(geom_, x_[cur_].ptr, stage_.ptr);
+  CUDA_CHECK(cudaGetLastError());
+  stats_.launches += 1;
+  CUDA_CHECK(cudaMemcpyAsync(out, stage_.ptr, pixels * 12, cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+void GridSolver::set_row_window(int lo, int hi) {
+  require_ready();
+  FPIE_REQUIRE(0 <= lo && lo <= hi && hi <= geom_.n, "row window outside the grid");
+  win_lo_ = lo;
+  win_hi_ = hi;
+}
+
+void GridSolver::band_view(int which, float **base, int64_t *plane_stride, int64_t *row_pitch, int *pad_rows,
+                           int *pad_cols) {
+  require_ready();
+  FPIE_REQUIRE(which == 0 || which == 1, "band_view: buffer index must be 0 or 1");
+  if (base) *base = x_[which].ptr;
+  if (plane_stride) *plane_stride = geom_.plane;
+  if (row_pitch) *row_pitch = geom_.pitch;
+  if (pad_rows) *pad_rows = geom_.padr;
+  if (pad_cols) *pad_cols = geom_.padc;
+}
+
+}  // namespace fpie

@@ -1,0 +1,95 @@
+// GridSolver: masked 5-point Jacobi on a padded planar fp32 layout (sm_100a).
+// Host-side class; the kernels live in grid_kernels.cu / grid_tiles.cu.
+#pragma once
+
+#include <vector>
+
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace fpie {
+
+// Register-tile geometry of the temporally blocked kernel: a CTA of NW warps
+// owns a TILE_H x TILE_W pixel tile of one channel plane; a thread owns
+// ROWS_PER_THREAD rows x 4 columns of it in registers.
+constexpr int TILE_W = 128;  // 32 lanes x float4
+constexpr int MAX_BLOCK_K = 16;
+constexpr int PAD_ROWS = 16;  // >= MAX_BLOCK_K
+constexpr int PAD_COLS = 32;  // >= round_up(MAX_BLOCK_K, 4), multiple of 32
+
+struct TileShape {
+  int rows_per_thread;
+  int warps;
+  int tile_h() const { return rows_per_thread * warps; }
+};
+
+struct GridStats {
+  int64_t unknowns = 0;
+  int64_t launches = 0;
+  int64_t active_tiles = 0;
+  int64_t total_tiles = 0;
+};
+
+class GridSolver {
+ public:
+  GridSolver(int device, cudaStream_t stream, int block_k, int variant);
+  ~GridSolver();
+
+  void reset(int n, int m, const int32_t *mask, int64_t mask_rs, int64_t mask_cs, const float *tgt,
+             const float *grad);
+  void reset_from_images(const uint8_t *src, int sh, int sw, const uint8_t *mask, int mh, int mw, int mc,
+                         const uint8_t *tgt, int th, int tw, int h0, int w0, int h1, int w1, int grad_mode,
+                         int64_t *out_n, int32_t *out_box4);
+  void sweeps_async(int iters);
+  void finish_async();
+  void sync();
+  void fetch(uint8_t *out_img, float *out_err3);
+  void step(int iters, uint8_t *out_img, float *out_err3);
+  void state(float *out);
+  void set_row_window(int lo, int hi);
+  void band_view(int which, float **base, int64_t *plane_stride, int64_t *row_pitch, int *pad_rows, int *pad_cols);
+
+  int device() const { return device_; }
+  int block_k() const { return block_k_; }
+  int current() const { return cur_; }
+  const GridStats &stats() const { return stats_; }
+  const PlaneGeom &geom() const { return geom_; }
+
+ private:
+  void require_ready() const;
+  void layout(int n, int m);
+  void build_tiles();
+  void after_state_loaded();
+  void make_tensor_maps();
+  static TileShape shape_for(int variant);
+
+  int device_;
+  cudaStream_t stream_;
+  int block_k_;
+  int halo_x_;
+  int variant_;
+  int sm_count_ = 0;
+  TileShape shape_{16, 12};
+
+  bool ready_ = false;
+  PlaneGeom geom_{};
+  int cur_ = 0;
+  int win_lo_ = 0, win_hi_ = 0;
+  DeviceBuffer<float> x_[2];
+  DeviceBuffer<float> hq_;
+  DeviceBuffer<uint32_t> bits_;
+  DeviceBuffer<float> stage_;
+  DeviceBuffer<int32_t> mask_stage_;
+  DeviceBuffer<uint8_t> img_;
+  DeviceBuffer<double> err_;  // [3] residual sums + [1] unknown count (as double)
+  DeviceBuffer<int4> tiles_;
+  DeviceBuffer<uint32_t> tile_flags_;
+  CUtensorMap tm_x_[2];
+  CUtensorMap tm_h_;
+  int n_tile_entries_ = 0;
+  double *host_err_ = nullptr;  // pinned [4]
+  GridStats stats_;
+};
+
+}  // namespace fpie

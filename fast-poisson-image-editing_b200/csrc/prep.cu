@@ -1,0 +1,86 @@
+// Upload + mask canonicalisation + bounding box for the fused resets.
+// Follows fpie/process.py:209-224 (Equ) == :338-351 (Grid).
+
+#include <climits>
+
+#include "prep.cuh"
+
+namespace fpie {
+
+// box = {min row, max row, min col, max col} of the canonical mask.
+__global__ void mask_bbox_kernel(BlendImages b, int *__restrict__ box) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long total = (long long)b.mh * b.mw;
+  int r = 0, c = 0;
+  bool on = false;
+  if (idx < total) {
+    r = (int)(idx / b.mw);
+    c = (int)(idx % b.mw);
+    on = canonical_mask_at(b, r, c);
+  }
+  const unsigned active = __ballot_sync(0xffffffffu, on);
+  if (!active) return;
+  const int rmin = __reduce_min_sync(0xffffffffu, on ? r : INT_MAX);
+  const int rmax = __reduce_max_sync(0xffffffffu, on ? r : INT_MIN);
+  const int cmin = __reduce_min_sync(0xffffffffu, on ? c : INT_MAX);
+  const int cmax = __reduce_max_sync(0xffffffffu, on ? c : INT_MIN);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&box[0], rmin);
+    atomicMax(&box[1], rmax);
+    atomicMin(&box[2], cmin);
+    atomicMax(&box[3], cmax);
+  }
+}
+
+void BlendUpload::release() {
+  src_.release();
+  mask_.release();
+  tgt_.release();
+}
+
+void BlendUpload::upload(cudaStream_t stream, const uint8_t *src, int sh, int sw, const uint8_t *mask, int mh, int mw,
+                         int mc, const uint8_t *tgt, int th, int tw, int h0, int w0, int h1, int w1, int mode) {
+  FPIE_REQUIRE(src && mask && tgt, "reset_from_images: null image");
+  FPIE_REQUIRE(sh > 0 && sw > 0 && mh > 0 && mw > 0 && th > 0 && tw > 0, "reset_from_images: empty image");
+  FPIE_REQUIRE(mc == 1 || mc == 3, "reset_from_images: mask must have 1 or 3 channels");
+  FPIE_REQUIRE(mode >= 0 && mode <= 2, "reset_from_images: unknown gradient mode");
+  const size_t sbytes = (size_t)sh * sw * 3, mbytes = (size_t)mh * mw * mc, tbytes = (size_t)th * tw * 3;
+  src_.resize(sbytes);
+  mask_.resize(mbytes);
+  tgt_.resize(tbytes);
+  box_.resize(4);
+  CUDA_CHECK(cudaMemcpyAsync(src_.ptr, src, sbytes, cudaMemcpyHostToDevice, stream));
+  CUDA_CHECK(cudaMemcpyAsync(mask_.ptr, mask, mbytes, cudaMemcpyHostToDevice, stream));
+  CUDA_CHECK(cudaMemcpyAsync(tgt_.ptr, tgt, tbytes, cudaMemcpyHostToDevice, stream));
+  const int init[4] = {INT_MAX, INT_MIN, INT_MAX, INT_MIN};
+  CUDA_CHECK(cudaMemcpyAsync(box_.ptr, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+
+  BlendImages b{};
+  b.src = src_.ptr;
+  b.mask = mask_.ptr;
+  b.tgt = tgt_.ptr;
+  b.sh = sh; b.sw = sw; b.mh = mh; b.mw = mw; b.mc = mc; b.th = th; b.tw = tw;
+  b.h0 = h0; b.w0 = w0; b.h1 = h1; b.w1 = w1;
+  b.mode = mode;
+  const long long total = (long long)mh * mw;
+  mask_bbox_kernel<<<(int)ceil_div(total, 256), 256, 0, stream>>>(b, box_.ptr);
+  CUDA_CHECK(cudaGetLastError());
+  int box[4];
+  CUDA_CHECK(cudaMemcpyAsync(box, box_.ptr, sizeof(box), cudaMemcpyDeviceToHost, stream));
+  CUDA_CHECK(cudaStreamSynchronize(stream));
+  // the reference dies with "zero-size array to reduction operation minimum" (process.py:220)
+  FPIE_REQUIRE(box[0] <= box[1], "reset: the mask is empty after thresholding and clearing its 1-pixel frame");
+  b.x0 = box[0] - 1;
+  b.y0 = box[2] - 1;
+  b.n = box[1] + 2 - b.x0;
+  b.m = box[3] + 2 - b.y0;
+  // the reference leaves these checks commented out (process.py:203-207) and
+  // then wraps around or throws from numpy; refuse instead
+  FPIE_REQUIRE(h0 + b.x0 >= 0 && w0 + b.y0 >= 0 && h0 + b.x0 + b.n <= sh && w0 + b.y0 + b.m <= sw,
+               "reset: the mask bounding box falls outside the source image");
+  FPIE_REQUIRE(h1 + b.x0 >= 0 && w1 + b.y0 >= 0 && h1 + b.x0 + b.n <= th && w1 + b.y0 + b.m <= tw,
+               "reset: the mask bounding box falls outside the target image");
+  img_ = b;
+}
+
+}  // namespace fpie

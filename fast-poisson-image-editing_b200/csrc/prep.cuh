@@ -1,0 +1,80 @@
+// Device-side Processor preprocessing shared by the fused resets
+// (fpie/process.py:209-224 / 338-351 mask canonicalisation, :113-122 mixgrad,
+// :241-246 / :362-376 gradient).
+#pragma once
+
+#include "common.cuh"
+
+namespace fpie {
+
+// The three uint8 images of one blend, resident on the device, plus the crop.
+struct BlendImages {
+  const uint8_t *src;
+  const uint8_t *mask;
+  const uint8_t *tgt;
+  int sh, sw;      // source rows / cols
+  int mh, mw, mc;  // mask rows / cols / channels (1 or 3)
+  int th, tw;      // target rows / cols
+  // crop box in mask coordinates and the offsets of mask (0,0) in src / tgt
+  int x0, y0, n, m;
+  int h0, w0, h1, w1;
+  int mode;  // FPIE_B200_GRAD_*
+};
+
+struct CropBox {
+  int x0, x1, y0, y1;  // in mask coordinates; crop = mask[x0:x1, y0:y1]
+};
+
+// Upload the images (host -> device buffers owned by the caller), find the
+// bounding box of the canonical mask and validate it against src / tgt.
+// Throws fpie::Error for an empty mask or a box that leaves an image.
+class BlendUpload {
+ public:
+  void upload(cudaStream_t stream, const uint8_t *src, int sh, int sw, const uint8_t *mask, int mh, int mw, int mc,
+              const uint8_t *tgt, int th, int tw, int h0, int w0, int h1, int w1, int mode);
+  const BlendImages &images() const { return img_; }
+  void release();
+
+ private:
+  DeviceBuffer<uint8_t> src_, mask_, tgt_;
+  DeviceBuffer<int> box_;
+  BlendImages img_{};
+};
+
+#ifdef __CUDACC__
+// canonical mask bit of mask-image pixel (r, c): threshold on the channel mean
+// (mean(-1) >= 128  <=>  sum >= 128 * channels, exact) and a cleared 1-px frame.
+__device__ __forceinline__ bool canonical_mask_at(const BlendImages &b, int r, int c) {
+  if (r <= 0 || c <= 0 || r >= b.mh - 1 || c >= b.mw - 1) return false;
+  const uint8_t *p = b.mask + ((long long)r * b.mw + c) * b.mc;
+  const int s = (b.mc == 3) ? (int)p[0] + (int)p[1] + (int)p[2] : (int)p[0];
+  return s >= 128 * b.mc;
+}
+
+__device__ __forceinline__ float mix_one(int mode, float a, float b) {
+  if (mode == 0) return a;               // src
+  if (mode == 1) return (a + b) * 0.5f;  // avg (exact: integers)
+  return (fabsf(a) < fabsf(b)) ? b : a;  // max: strict <, ties keep the source difference
+}
+
+// grad(p) for crop pixel (i, j), channel ch: sum over the four neighbours q of
+// mix(src(p) - src(q), tgt(p) - tgt(q)).  All operands are small integers or
+// halves, so the fp32 sum is exact in any order.
+__device__ __forceinline__ float pixel_gradient(const BlendImages &b, int i, int j, int ch) {
+  const long long sp = ((long long)(b.h0 + b.x0 + i) * b.sw + (b.w0 + b.y0 + j)) * 3 + ch;
+  const long long tp = ((long long)(b.h1 + b.x0 + i) * b.tw + (b.w1 + b.y0 + j)) * 3 + ch;
+  const float sc = (float)b.src[sp], tc = (float)b.tgt[tp];
+  const long long so[4] = {-(long long)b.sw * 3, (long long)b.sw * 3, -3, 3};
+  const long long to[4] = {-(long long)b.tw * 3, (long long)b.tw * 3, -3, 3};
+  float g = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) g += mix_one(b.mode, sc - (float)b.src[sp + so[k]], tc - (float)b.tgt[tp + to[k]]);
+  return g;
+}
+
+__device__ __forceinline__ float target_at(const BlendImages &b, int i, int j, int ch) {
+  return (float)b.tgt[((long long)(b.h1 + b.x0 + i) * b.tw + (b.w1 + b.y0 + j)) * 3 + ch];
+}
+#endif
+
+}  // namespace fpie

@@ -1,0 +1,103 @@
+"""ctypes binding of ``libfpie_b200.so`` (C ABI: include/fpie_b200.h).
+
+There is no CPU fallback: if the shared library is missing or cannot be
+loaded, importing a solver raises ``ImportError`` -- the same signal the
+reference uses to drop a backend (fpie/process.py:77-83).
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libfpie_b200.so")
+
+c_int = ctypes.c_int
+c_i64 = ctypes.c_int64
+c_void_p = ctypes.c_void_p
+P = ctypes.POINTER
+i32p, f32p, u8p, i64p, intp = P(ctypes.c_int32), P(ctypes.c_float), P(ctypes.c_uint8), P(c_i64), P(c_int)
+
+# name -> (argtypes); every function returns int except the two noted below.
+SIGNATURES = {
+    "fpie_b200_abi_version": [],
+    "fpie_b200_device_count": [],
+    "fpie_b200_device_info": [c_int, ctypes.c_char_p, c_int, intp, intp, intp],
+    "fpie_b200_grid_create": [c_int, c_void_p, c_int, c_int, P(c_void_p)],
+    "fpie_b200_grid_destroy": [c_void_p],
+    "fpie_b200_grid_reset": [c_void_p, c_int, c_int, i32p, c_i64, c_i64, f32p, f32p],
+    "fpie_b200_grid_step": [c_void_p, c_int, u8p, f32p],
+    "fpie_b200_grid_state": [c_void_p, f32p],
+    "fpie_b200_grid_sweeps_async": [c_void_p, c_int],
+    "fpie_b200_grid_finish_async": [c_void_p],
+    "fpie_b200_grid_sync": [c_void_p],
+    "fpie_b200_grid_fetch": [c_void_p, u8p, f32p],
+    "fpie_b200_grid_info": [c_void_p, i64p, i64p, intp, i64p, i64p],
+    "fpie_b200_grid_reset_from_images": [c_void_p, u8p, c_int, c_int, u8p, c_int, c_int, c_int, u8p, c_int, c_int,
+                                         c_int, c_int, c_int, c_int, c_int, i64p, i32p],
+    "fpie_b200_grid_band_view": [c_void_p, c_int, P(c_void_p), i64p, i64p, intp, intp],
+    "fpie_b200_grid_band_current": [c_void_p, intp],
+    "fpie_b200_grid_set_row_window": [c_void_p, c_int, c_int],
+    "fpie_b200_equ_create": [c_int, c_void_p, c_int, P(c_void_p)],
+    "fpie_b200_equ_destroy": [c_void_p],
+    "fpie_b200_equ_partition": [c_void_p, c_int, c_int, i32p, c_i64, c_i64, i32p],
+    "fpie_b200_equ_reset": [c_void_p, c_i64, i32p, f32p, f32p],
+    "fpie_b200_equ_step": [c_void_p, c_int, u8p, f32p],
+    "fpie_b200_equ_state": [c_void_p, f32p],
+    "fpie_b200_equ_sweeps_async": [c_void_p, c_int],
+    "fpie_b200_equ_finish_async": [c_void_p],
+    "fpie_b200_equ_sync": [c_void_p],
+    "fpie_b200_equ_fetch": [c_void_p, u8p, f32p],
+    "fpie_b200_equ_info": [c_void_p, i64p, i64p],
+    "fpie_b200_equ_reset_from_images": [c_void_p, u8p, c_int, c_int, u8p, c_int, c_int, c_int, u8p, c_int, c_int,
+                                        c_int, c_int, c_int, c_int, c_int, i64p, i32p],
+    "fpie_b200_equ_step_paste": [c_void_p, c_int, u8p, f32p],
+    "fpie_b200_equ_system": [c_void_p, i32p, f32p, f32p],
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise ImportError if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m fpie_b200._build` "
+            "(needs nvcc; fpie_b200 has no CPU fallback)"
+        )
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as exc:  # e.g. libcudart not found
+        raise ImportError(f"cannot load {LIB_PATH}: {exc}") from exc
+    lib.fpie_b200_last_error.restype = ctypes.c_char_p
+    lib.fpie_b200_last_error.argtypes = []
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = c_int
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    """Turn a non-zero status into RuntimeError, as pybind11 does for the
+    reference's std::runtime_error (fpie/core/base_solver.h:63-74)."""
+    if rc != 0:
+        msg = load().fpie_b200_last_error().decode("utf-8", "replace")
+        raise RuntimeError(msg or f"fpie_b200 call failed with status {rc}")
+
+
+def current_stream_handle(device: int) -> int:
+    """The raw cudaStream_t of torch's current stream on ``device`` (0 = the
+    default stream when torch is not importable)."""
+    try:
+        import torch
+    except ImportError:
+        return 0
+    if not torch.cuda.is_available():
+        return 0
+    return int(torch.cuda.current_stream(device).cuda_stream)

@@ -1,0 +1,95 @@
+"""Processor layer for the b200 backend.
+
+Mirrors ``fpie.process.EquProcessor`` / ``GridProcessor`` (fpie/process.py:146-395):
+same constructor argument order (fpie/cli.py:16-32 passes them positionally),
+``reset(src, mask, tgt, mask_on_src, mask_on_tgt) -> int``, ``sync()`` and
+``step(iteration) -> (uint8 target image, err[3])``, returning the same
+full-size target buffer on every call (process.py:278-279, 393-394).
+
+The difference is where ``reset`` runs: the reference builds the linear
+system / gradient field on the host with numpy and hands fp32 arrays to the
+core; here ``reset`` uploads the three uint8 images once and every step of
+the preprocessing (mask threshold, frame clear, bounding box, id scan, A/X/B
+or gradient build) is a CUDA kernel (``*_reset_from_images`` in
+include/fpie_b200.h).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .solver import EquSolver, GridSolver
+
+BACKEND = "b200"
+GRADIENTS = ("max", "src", "avg")
+
+
+class BaseProcessor:
+    """Common state of both processors (fpie/process.py:86-143)."""
+
+    def __init__(self, gradient: str, backend: str, core):
+        if gradient not in GRADIENTS:
+            raise ValueError(f"gradient must be one of {GRADIENTS}, got {gradient!r}")
+        if backend != BACKEND:
+            raise AssertionError(f"Invalid backend {backend}.")  # process.py:105
+        self.gradient = gradient
+        self.backend = backend
+        self.core = core
+        self.rank = 0
+        self.root = True
+        self.tgt = None
+
+    def sync(self) -> None:
+        self.core.sync()
+
+    @staticmethod
+    def _check_images(src, mask, tgt):
+        for name, img in (("src", src), ("tgt", tgt)):
+            if img.ndim != 3 or img.shape[2] != 3:
+                raise ValueError(f"{name} must be [rows, cols, 3]")
+        if mask.ndim not in (2, 3):
+            raise ValueError("mask must be [rows, cols] or [rows, cols, channels]")
+
+
+class EquProcessor(BaseProcessor):
+    """PIE Jacobi equation processor on the b200 core (fpie/process.py:146-280)."""
+
+    def __init__(self, gradient: str = "max", backend: str = BACKEND, n_cpu: int = 0, min_interval: int = 100,
+                 block_size: int = 256, device: int | None = None):
+        super().__init__(gradient, backend, EquSolver(block_size, device=device))
+
+    def reset(self, src, mask, tgt, mask_on_src=(0, 0), mask_on_tgt=(0, 0)) -> int:
+        src, mask, tgt = np.asarray(src), np.asarray(mask), np.asarray(tgt)
+        self._check_images(src, mask, tgt)
+        n, box = self.core.reset_from_images(src, mask, tgt, mask_on_src, mask_on_tgt, self.gradient)
+        self.box = box
+        self.tgt = np.array(tgt, dtype=np.uint8, copy=True)  # process.py:268
+        return n
+
+    def step(self, iteration: int):
+        crop, err = self.core.step_paste(iteration)
+        x0, x1, y0, y1 = self.box
+        self.tgt[x0:x1, y0:y1] = crop  # pixels outside the mask already hold the target
+        return self.tgt, err
+
+
+class GridProcessor(BaseProcessor):
+    """PIE grid processor on the b200 core (fpie/process.py:283-395)."""
+
+    def __init__(self, gradient: str = "max", backend: str = BACKEND, n_cpu: int = 0, min_interval: int = 100,
+                 block_size: int = 256, grid_x: int = 8, grid_y: int = 8, device: int | None = None,
+                 block_k: int = 0):
+        super().__init__(gradient, backend, GridSolver(grid_x, grid_y, device=device, block_k=block_k))
+
+    def reset(self, src, mask, tgt, mask_on_src=(0, 0), mask_on_tgt=(0, 0)) -> int:
+        src, mask, tgt = np.asarray(src), np.asarray(mask), np.asarray(tgt)
+        self._check_images(src, mask, tgt)
+        n, box = self.core.reset_from_images(src, mask, tgt, mask_on_src, mask_on_tgt, self.gradient)
+        self.x0, self.x1, self.y0, self.y1 = box
+        self.tgt = np.array(tgt, dtype=np.uint8, copy=True)  # process.py:384
+        return n
+
+    def step(self, iteration: int):
+        img, err = self.core.step(iteration)
+        self.tgt[self.x0 : self.x1, self.y0 : self.y1] = img  # process.py:393
+        return self.tgt, err

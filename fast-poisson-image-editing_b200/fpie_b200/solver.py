@@ -1,0 +1,334 @@
+"""Core solvers with the reference's interface.
+
+``EquSolver`` / ``GridSolver`` mirror the classes every fpie backend exports
+(pybind11 classes in fpie/core/cuda/solver.cc:3-15, Python classes in
+fpie/np_solver.py): ``partition`` (Equ only), ``reset``, ``sync``,
+``step(iteration) -> (uint8 image, float32 err[3])``.  All compute happens in
+hand-written sm_100a CUDA behind the C ABI of ``include/fpie_b200.h``; numpy
+arrays are only the boundary format.
+"""
+
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+GRAD_CODE = {"src": 0, "avg": 1, "max": 2}
+
+
+def _ptr(a: np.ndarray, ct):
+    return a.ctypes.data_as(ctypes.POINTER(ct))
+
+
+def _mask_view(mask) -> np.ndarray:
+    """int32 2-D view whose rows are contiguous (the Processor hands over a
+    non-contiguous slice, fpie/process.py:224/351; rows stay strided)."""
+    m = np.asarray(mask)
+    if m.ndim != 2:
+        raise ValueError("mask must be a 2-D array")
+    if m.dtype != np.int32 or m.strides[1] != 4 or m.strides[0] % 4 != 0 or m.strides[0] < 4 * m.shape[1]:
+        m = np.ascontiguousarray(m, dtype=np.int32)
+    return m
+
+
+def _as_u8_image(img, what: str) -> np.ndarray:
+    a = np.ascontiguousarray(img, dtype=np.uint8)
+    if a.ndim != 3 or a.shape[2] != 3:
+        raise ValueError(f"{what} must be a uint8 [rows, cols, 3] image")
+    return a
+
+
+def _as_u8_mask(mask) -> np.ndarray:
+    a = np.ascontiguousarray(mask, dtype=np.uint8)
+    if a.ndim == 2:
+        return a[:, :, None]
+    if a.ndim == 3 and a.shape[2] in (1, 3):
+        return a
+    raise ValueError("mask must be uint8 [rows, cols] or [rows, cols, 1|3]")
+
+
+def default_device() -> int:
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            return int(torch.cuda.current_device())
+    except ImportError:
+        pass
+    return 0
+
+
+class _Handle:
+    def __init__(self):
+        self._h = ctypes.c_void_p()
+        self._lib = _lib.load()
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise RuntimeError("solver has been closed")
+        return self._h
+
+
+class GridSolver(_Handle):
+    """Drop-in for ``core_cuda.GridSolver(grid_x, grid_y)`` (fpie/process.py:312-313).
+
+    ``grid_x`` / ``grid_y`` are accepted for signature compatibility; the tile
+    geometry of the temporally blocked kernel is fixed by the register layout.
+    ``block_k`` = sweeps fused per pass over HBM (default 8).
+    """
+
+    def __init__(self, grid_x: int = 8, grid_y: int = 8, device: int | None = None, block_k: int = 0,
+                 variant: int = 0):
+        super().__init__()
+        self.grid_x, self.grid_y = int(grid_x), int(grid_y)
+        self.device = default_device() if device is None else int(device)
+        self.shape = None
+        stream = _lib.current_stream_handle(self.device)
+        _lib.check(self._lib.fpie_b200_grid_create(self.device, ctypes.c_void_p(stream), int(block_k), int(variant),
+                                                   ctypes.byref(self._h)))
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.fpie_b200_grid_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- reference interface -------------------------------------------------
+    def reset(self, N, mask, tgt, grad) -> None:
+        """``reset(N, mask i32[n,m], tgt f32[n,m,3], grad f32[n,m,3])``; ``N`` is
+        ignored exactly as in the reference (fpie/core/base_solver.h:101-113)."""
+        m = _mask_view(mask)
+        t = np.ascontiguousarray(tgt, dtype=np.float32)
+        g = np.ascontiguousarray(grad, dtype=np.float32)
+        n, w = m.shape
+        if t.shape != (n, w, 3) or g.shape != (n, w, 3):
+            raise ValueError("tgt and grad must have shape mask.shape + (3,)")
+        _lib.check(self._lib.fpie_b200_grid_reset(self.handle, n, w, _ptr(m, ctypes.c_int32), m.strides[0] // 4, 1,
+                                                  _ptr(t, ctypes.c_float), _ptr(g, ctypes.c_float)))
+        self.shape = (n, w)
+
+    def sync(self) -> None:
+        """No-op in the reference for every backend but mpi (base_solver.h:142)."""
+
+    def step(self, iteration: int):
+        n, w = self._need_shape()
+        img = np.empty((n, w, 3), np.uint8)
+        err = np.empty(3, np.float32)
+        _lib.check(self._lib.fpie_b200_grid_step(self.handle, int(iteration), _ptr(img, ctypes.c_uint8),
+                                                 _ptr(err, ctypes.c_float)))
+        return img, err
+
+    # -- extras ---------------------------------------------------------------
+    def reset_from_images(self, src, mask, tgt, mask_on_src, mask_on_tgt, gradient: str = "max"):
+        """Fused ``GridProcessor.reset`` on the device (fpie/process.py:321-386).
+        Returns ``(n_vars, (x0, x1, y0, y1))`` with the box in target coordinates."""
+        s, t, mk = _as_u8_image(src, "src"), _as_u8_image(tgt, "tgt"), _as_u8_mask(mask)
+        out_n = ctypes.c_int64()
+        box = np.zeros(4, np.int32)
+        _lib.check(self._lib.fpie_b200_grid_reset_from_images(
+            self.handle, _ptr(s, ctypes.c_uint8), s.shape[0], s.shape[1], _ptr(mk, ctypes.c_uint8), mk.shape[0],
+            mk.shape[1], mk.shape[2], _ptr(t, ctypes.c_uint8), t.shape[0], t.shape[1], int(mask_on_src[0]),
+            int(mask_on_src[1]), int(mask_on_tgt[0]), int(mask_on_tgt[1]), GRAD_CODE[gradient], ctypes.byref(out_n),
+            _ptr(box, ctypes.c_int32)))
+        self.shape = (int(box[1] - box[0]), int(box[3] - box[2]))
+        return int(out_n.value), tuple(int(v) for v in box)
+
+    def state(self) -> np.ndarray:
+        n, w = self._need_shape()
+        out = np.empty((n, w, 3), np.float32)
+        _lib.check(self._lib.fpie_b200_grid_state(self.handle, _ptr(out, ctypes.c_float)))
+        return out
+
+    def sweeps_async(self, iteration: int) -> None:
+        _lib.check(self._lib.fpie_b200_grid_sweeps_async(self.handle, int(iteration)))
+
+    def finish_async(self) -> None:
+        _lib.check(self._lib.fpie_b200_grid_finish_async(self.handle))
+
+    def wait(self) -> None:
+        _lib.check(self._lib.fpie_b200_grid_sync(self.handle))
+
+    def fetch(self, img: np.ndarray | None = None):
+        n, w = self._need_shape()
+        if img is None:
+            img = np.empty((n, w, 3), np.uint8)
+        err = np.empty(3, np.float32)
+        _lib.check(self._lib.fpie_b200_grid_fetch(self.handle, _ptr(img, ctypes.c_uint8), _ptr(err, ctypes.c_float)))
+        return img, err
+
+    def info(self) -> dict:
+        unk, launches, act, tot = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        k = ctypes.c_int()
+        _lib.check(self._lib.fpie_b200_grid_info(self.handle, ctypes.byref(unk), ctypes.byref(launches),
+                                                 ctypes.byref(k), ctypes.byref(act), ctypes.byref(tot)))
+        return dict(unknowns=unk.value, launches=launches.value, block_k=k.value, active_tiles=act.value,
+                    total_tiles=tot.value)
+
+    def set_row_window(self, lo: int, hi: int) -> None:
+        _lib.check(self._lib.fpie_b200_grid_set_row_window(self.handle, int(lo), int(hi)))
+
+    def band_view(self, which: int):
+        base = ctypes.c_void_p()
+        plane, pitch = ctypes.c_int64(), ctypes.c_int64()
+        padr, padc = ctypes.c_int(), ctypes.c_int()
+        _lib.check(self._lib.fpie_b200_grid_band_view(self.handle, int(which), ctypes.byref(base), ctypes.byref(plane),
+                                                      ctypes.byref(pitch), ctypes.byref(padr), ctypes.byref(padc)))
+        return dict(base=base.value, plane=plane.value, pitch=pitch.value, pad_rows=padr.value, pad_cols=padc.value)
+
+    def current_buffer(self) -> int:
+        which = ctypes.c_int()
+        _lib.check(self._lib.fpie_b200_grid_band_current(self.handle, ctypes.byref(which)))
+        return which.value
+
+    def _need_shape(self):
+        if self.shape is None:
+            raise RuntimeError("GridSolver: step/state called before reset")
+        return self.shape
+
+
+class EquSolver(_Handle):
+    """Drop-in for ``core_cuda.EquSolver(block_size)`` (fpie/process.py:173-174)."""
+
+    def __init__(self, block_size: int = 256, device: int | None = None):
+        super().__init__()
+        self.device = default_device() if device is None else int(device)
+        self.N = 0
+        self.crop_shape = None
+        stream = _lib.current_stream_handle(self.device)
+        _lib.check(self._lib.fpie_b200_equ_create(self.device, ctypes.c_void_p(stream), int(block_size),
+                                                  ctypes.byref(self._h)))
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.fpie_b200_equ_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- reference interface -------------------------------------------------
+    def partition(self, mask) -> np.ndarray:
+        """Row-major ids of masked pixels by a device prefix scan
+        (fpie/core/cuda/equ.cu:36-54; fpie/np_solver.py:14-16)."""
+        m = _mask_view(mask)
+        ids = np.empty(m.shape, np.int32)
+        _lib.check(self._lib.fpie_b200_equ_partition(self.handle, m.shape[0], m.shape[1], _ptr(m, ctypes.c_int32),
+                                                     m.strides[0] // 4, 1, _ptr(ids, ctypes.c_int32)))
+        return ids
+
+    def reset(self, N, A, X, B) -> None:
+        N = int(N)
+        a = np.ascontiguousarray(A, dtype=np.int32)
+        x = np.ascontiguousarray(X, dtype=np.float32)
+        b = np.ascontiguousarray(B, dtype=np.float32)
+        if a.shape != (N, 4) or x.shape != (N, 3) or b.shape != (N, 3):
+            raise ValueError("expected A[N,4], X[N,3], B[N,3]")
+        _lib.check(self._lib.fpie_b200_equ_reset(self.handle, N, _ptr(a, ctypes.c_int32), _ptr(x, ctypes.c_float),
+                                                 _ptr(b, ctypes.c_float)))
+        self.N = N
+        self.crop_shape = None
+
+    def sync(self) -> None:
+        """No-op, as in the reference (base_solver.h:61)."""
+
+    def step(self, iteration: int):
+        self._need_reset()
+        img = np.empty((self.N, 3), np.uint8)
+        err = np.empty(3, np.float32)
+        _lib.check(self._lib.fpie_b200_equ_step(self.handle, int(iteration), _ptr(img, ctypes.c_uint8),
+                                                _ptr(err, ctypes.c_float)))
+        return img, err
+
+    # -- extras ---------------------------------------------------------------
+    def reset_from_images(self, src, mask, tgt, mask_on_src, mask_on_tgt, gradient: str = "max"):
+        """Fused ``EquProcessor.reset`` on the device (fpie/process.py:192-271).
+        Returns ``(N, (x0, x1, y0, y1))`` with the box in target coordinates."""
+        s, t, mk = _as_u8_image(src, "src"), _as_u8_image(tgt, "tgt"), _as_u8_mask(mask)
+        out_n = ctypes.c_int64()
+        box = np.zeros(4, np.int32)
+        _lib.check(self._lib.fpie_b200_equ_reset_from_images(
+            self.handle, _ptr(s, ctypes.c_uint8), s.shape[0], s.shape[1], _ptr(mk, ctypes.c_uint8), mk.shape[0],
+            mk.shape[1], mk.shape[2], _ptr(t, ctypes.c_uint8), t.shape[0], t.shape[1], int(mask_on_src[0]),
+            int(mask_on_src[1]), int(mask_on_tgt[0]), int(mask_on_tgt[1]), GRAD_CODE[gradient], ctypes.byref(out_n),
+            _ptr(box, ctypes.c_int32)))
+        self.N = int(out_n.value)
+        self.crop_shape = (int(box[1] - box[0]), int(box[3] - box[2]))
+        return self.N, tuple(int(v) for v in box)
+
+    def step_paste(self, iteration: int):
+        """``step`` + the Processor's scatter (process.py:273-280), on the device:
+        returns the uint8 crop ``[x1-x0, y1-y0, 3]`` and ``err``."""
+        if self.crop_shape is None:
+            raise RuntimeError("step_paste needs reset_from_images")
+        crop = np.empty(self.crop_shape + (3,), np.uint8)
+        err = np.empty(3, np.float32)
+        _lib.check(self._lib.fpie_b200_equ_step_paste(self.handle, int(iteration), _ptr(crop, ctypes.c_uint8),
+                                                      _ptr(err, ctypes.c_float)))
+        return crop, err
+
+    def state(self) -> np.ndarray:
+        self._need_reset()
+        out = np.empty((self.N, 3), np.float32)
+        _lib.check(self._lib.fpie_b200_equ_state(self.handle, _ptr(out, ctypes.c_float)))
+        return out
+
+    def system(self):
+        """(A, X, B) as the device holds them (parity checks of the fused reset)."""
+        self._need_reset()
+        A = np.empty((self.N, 4), np.int32)
+        X = np.empty((self.N, 3), np.float32)
+        B = np.empty((self.N, 3), np.float32)
+        _lib.check(self._lib.fpie_b200_equ_system(self.handle, _ptr(A, ctypes.c_int32), _ptr(X, ctypes.c_float),
+                                                  _ptr(B, ctypes.c_float)))
+        return A, X, B
+
+    def sweeps_async(self, iteration: int) -> None:
+        _lib.check(self._lib.fpie_b200_equ_sweeps_async(self.handle, int(iteration)))
+
+    def finish_async(self) -> None:
+        _lib.check(self._lib.fpie_b200_equ_finish_async(self.handle))
+
+    def wait(self) -> None:
+        _lib.check(self._lib.fpie_b200_equ_sync(self.handle))
+
+    def fetch(self, img: np.ndarray | None = None):
+        self._need_reset()
+        if img is None:
+            img = np.empty((self.N, 3), np.uint8)
+        err = np.empty(3, np.float32)
+        _lib.check(self._lib.fpie_b200_equ_fetch(self.handle, _ptr(img, ctypes.c_uint8), _ptr(err, ctypes.c_float)))
+        return img, err
+
+    def info(self) -> dict:
+        unk, launches = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(self._lib.fpie_b200_equ_info(self.handle, ctypes.byref(unk), ctypes.byref(launches)))
+        return dict(unknowns=unk.value, launches=launches.value)
+
+    def _need_reset(self):
+        if self.N <= 0:
+            raise RuntimeError("EquSolver: step/state called before reset")
+
+
+def device_count() -> int:
+    return int(_lib.load().fpie_b200_device_count())
+
+
+def device_info(device: int = 0) -> dict:
+    lib = _lib.load()
+    name = ctypes.create_string_buffer(256)
+    sm, major, minor = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _lib.check(lib.fpie_b200_device_info(int(device), name, 256, ctypes.byref(sm), ctypes.byref(major),
+                                         ctypes.byref(minor)))
+    return dict(name=name.value.decode(), sm_count=sm.value, cc=(major.value, minor.value))

@@ -1,0 +1,178 @@
+/*
+ * fpie_b200 -- C ABI of the B200-native Jacobi Poisson backend.
+ *
+ * This is the drop-in boundary for the one hot path of
+ * Trinkle23897/Fast-Poisson-Image-Editing (fpie 0.3.2): the core-solver
+ * interface `partition / reset / sync / step` that fpie's Processor layer
+ * drives (fpie/process.py:138,187,270,275,385,390) and that the reference
+ * binds with pybind11 per backend (fpie/core/cuda/solver.cc:3-15,
+ * fpie/core/openmp/solver.cc:3-15; state and numpy->C copies in
+ * fpie/core/base_solver.h:12-75 and :77-152).
+ *
+ * Conventions
+ *   - plain C types only: pointers + sizes, no numpy/torch/pybind types;
+ *   - every entry point returns 0 on success and a non-zero code on failure;
+ *     `fpie_b200_last_error()` then returns a thread-local message (the
+ *     reference checks no CUDA call at all: fpie/core/cuda/equ.cu:56-74);
+ *   - "host" pointers may be pageable or pinned; "dev" pointers are CUDA
+ *     device pointers on the solver's device;
+ *   - all device work of a solver is enqueued on the `stream` given at
+ *     creation (a `cudaStream_t` passed as `void*`; NULL = the legacy default
+ *     stream), so a caller can bracket it with its own events;
+ *   - image layouts at the boundary are the reference's: interleaved
+ *     `[rows, cols, 3]`, float32 state, int32 mask / ids, uint8 images.
+ *
+ * There is no CPU fallback: without a CUDA device `*_create` fails.
+ */
+#ifndef FPIE_B200_H_
+#define FPIE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPIE_B200_ABI_VERSION 1
+
+/* gradient mixing modes of BaseProcessor.mixgrad (fpie/process.py:113-122) */
+#define FPIE_B200_GRAD_SRC 0
+#define FPIE_B200_GRAD_AVG 1
+#define FPIE_B200_GRAD_MAX 2
+
+typedef struct fpie_b200_grid fpie_b200_grid;
+typedef struct fpie_b200_equ fpie_b200_equ;
+
+/* ---- library ----------------------------------------------------------- */
+
+int fpie_b200_abi_version(void);
+/* Message of the last failing call on this thread ("" if none). */
+const char *fpie_b200_last_error(void);
+/* Number of CUDA devices (0 when there is no usable driver/GPU). */
+int fpie_b200_device_count(void);
+/* Name / SM count / compute capability of a device, for logs
+ * (the reference prints a device table from every constructor:
+ * fpie/core/cuda/utils.cu:5-22; here it is a query, not a side effect). */
+int fpie_b200_device_info(int device, char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---- GridSolver ---------------------------------------------------------
+ * Replaces CudaGridSolver (fpie/core/cuda/grid.cu:7-153) behind the
+ * GridSolver interface of fpie/core/base_solver.h:77-152. */
+
+/* GridSolver(grid_x, grid_y) constructor (fpie/process.py:312-313).
+ * `block_k` = Jacobi sweeps fused per pass over HBM (temporal blocking depth,
+ * 1..16; 0 = default); `variant` selects a kernel family for testing
+ * (0 = default, 1 = one-sweep-per-launch kernels only). */
+int fpie_b200_grid_create(int device, void *stream, int block_k, int variant, fpie_b200_grid **out);
+int fpie_b200_grid_destroy(fpie_b200_grid *g);
+
+/* GridSolver::reset(n, mask, tgt, grad) (base_solver.h:101-140 + grid.cu:33-52).
+ * mask: int32 [n, m] with element strides (the Processor passes a
+ * non-contiguous view, fpie/process.py:351); tgt, grad: float32 [n, m, 3]
+ * C-contiguous.  Inputs are copied; mask pixels on the outer frame of the
+ * grid are treated as unmasked (the Processor guarantees a zero frame,
+ * process.py:342-351; the reference would read out of bounds otherwise). */
+int fpie_b200_grid_reset(fpie_b200_grid *g, int n, int m, const int32_t *mask, int64_t mask_row_stride,
+                         int64_t mask_col_stride, const float *tgt, const float *grad);
+
+/* GridSolver::step(iteration) -> (img u8 [n, m, 3], err f32 [3])
+ * (grid.cu:133-153).  Runs exactly `iters` more true-Jacobi sweeps on the
+ * persistent state (np_solver.py:81-88 semantics), then the residual
+ * (np_solver.py:90-96) and the clamp+truncate to uint8 (grid.cu:115-131).
+ * Blocks until the results are in the host buffers. */
+int fpie_b200_grid_step(fpie_b200_grid *g, int iters, uint8_t *out_img, float *out_err3);
+
+/* The fp32 state [n, m, 3] (the reference never exposes it from native
+ * cores; needed for the fp32 parity check). */
+int fpie_b200_grid_state(fpie_b200_grid *g, float *out_state);
+
+/* Device-resident pieces of step(), for measurement and for callers that
+ * keep results on the device: enqueue `iters` sweeps (no sync, no copy);
+ * enqueue residual + u8 conversion; wait for the stream; copy results. */
+int fpie_b200_grid_sweeps_async(fpie_b200_grid *g, int iters);
+int fpie_b200_grid_finish_async(fpie_b200_grid *g);
+int fpie_b200_grid_sync(fpie_b200_grid *g);
+int fpie_b200_grid_fetch(fpie_b200_grid *g, uint8_t *out_img, float *out_err3);
+
+/* Number of masked pixels (unknowns) and kernel launches issued so far. */
+int fpie_b200_grid_info(fpie_b200_grid *g, int64_t *unknowns, int64_t *launches, int *block_k,
+                        int64_t *active_tiles, int64_t *total_tiles);
+
+/* Fused Processor-level reset (GridProcessor.reset, fpie/process.py:321-386)
+ * executed on the device from uint8 images: mask threshold / frame clear /
+ * bounding box, crop, mixed gradient, state upload.
+ * src [sh, sw, 3], tgt [th, tw, 3], mask [mh, mw, mc] with mc in {1, 3};
+ * (h0, w0) / (h1, w1) = position of mask pixel (0,0) in src / tgt.
+ * out_box = {x0, x1, y0, y1} of the solved crop in target coordinates;
+ * returns the crop size n*m in *out_n ("# of vars" of the reference). */
+int fpie_b200_grid_reset_from_images(fpie_b200_grid *g, const uint8_t *src, int sh, int sw, const uint8_t *mask,
+                                     int mh, int mw, int mc, const uint8_t *tgt, int th, int tw, int h0, int w0,
+                                     int h1, int w1, int grad_mode, int64_t *out_n, int32_t *out_box4);
+
+/* Row-band sharding (multi-GPU): treat this solver as one band of a taller
+ * grid.  After reset, `halo` rows above / below the band are exchanged by the
+ * caller every `halo` sweeps (NCCL send/recv on the returned device
+ * pointers); see fpie_b200/band.py.  rows are in grid coordinates of this
+ * band's local problem.  Pointers are to float32 planes: plane p (channel)
+ * row r starts at base + p*plane_stride + r*row_pitch (in floats). */
+int fpie_b200_grid_band_view(fpie_b200_grid *g, int which_buffer, float **dev_base, int64_t *plane_stride,
+                             int64_t *row_pitch, int *pad_rows, int *pad_cols);
+int fpie_b200_grid_band_current(fpie_b200_grid *g, int *which_buffer);
+/* Restrict the sweeps of the next fpie_b200_grid_sweeps_async calls to grid
+ * rows [row_lo, row_hi) (the shrinking trapezoid between halo exchanges). */
+int fpie_b200_grid_set_row_window(fpie_b200_grid *g, int row_lo, int row_hi);
+
+/* ---- EquSolver ----------------------------------------------------------
+ * Replaces CudaEquSolver (fpie/core/cuda/equ.cu:7-211) behind the EquSolver
+ * interface of fpie/core/base_solver.h:12-75. */
+
+/* EquSolver(block_size) constructor (fpie/process.py:173-174). */
+int fpie_b200_equ_create(int device, void *stream, int block_size, fpie_b200_equ **out);
+int fpie_b200_equ_destroy(fpie_b200_equ *e);
+
+/* EquSolver::partition(mask) -> ids (equ.cu:36-54; np_solver.py:14-16):
+ * row-major inclusive count of mask > 0, computed by a device prefix scan.
+ * mask int32 [n, m] with element strides; ids int32 [n, m] C-contiguous.
+ * ids on unmasked pixels hold the running count (the caller zeroes them,
+ * process.py:188). */
+int fpie_b200_equ_partition(fpie_b200_equ *e, int n, int m, const int32_t *mask, int64_t mask_row_stride,
+                            int64_t mask_col_stride, int32_t *out_ids);
+
+/* EquSolver::reset(N, A, X, B) (base_solver.h:27-59 + equ.cu:56-74).
+ * A int32 [N, 4] (up, down, left, right; 0 = constant-zero row), X, B float32
+ * [N, 3], C-contiguous; row 0 is the zero constant.  Inputs are copied.
+ * Entries of A outside [0, N) are rejected. */
+int fpie_b200_equ_reset(fpie_b200_equ *e, int64_t N, const int32_t *A, const float *X, const float *B);
+
+/* EquSolver::step(iteration) -> (img u8 [N, 3], err f32 [3]) (equ.cu:189-211),
+ * true Jacobi (np_solver.py:33-50 semantics). */
+int fpie_b200_equ_step(fpie_b200_equ *e, int iters, uint8_t *out_img, float *out_err3);
+int fpie_b200_equ_state(fpie_b200_equ *e, float *out_state);
+
+int fpie_b200_equ_sweeps_async(fpie_b200_equ *e, int iters);
+int fpie_b200_equ_finish_async(fpie_b200_equ *e);
+int fpie_b200_equ_sync(fpie_b200_equ *e);
+int fpie_b200_equ_fetch(fpie_b200_equ *e, uint8_t *out_img, float *out_err3);
+int fpie_b200_equ_info(fpie_b200_equ *e, int64_t *unknowns, int64_t *launches);
+
+/* Fused Processor-level reset (EquProcessor.reset, fpie/process.py:192-271)
+ * on the device: mask canonicalisation, partition scan, index compaction and
+ * the A / X / B build for the three gradient modes.  Returns N = K + 1 in
+ * *out_n and the crop box in target coordinates.  The scatter list
+ * (process.py:269) stays on the device: see fpie_b200_equ_step_paste. */
+int fpie_b200_equ_reset_from_images(fpie_b200_equ *e, const uint8_t *src, int sh, int sw, const uint8_t *mask, int mh,
+                                    int mw, int mc, const uint8_t *tgt, int th, int tw, int h0, int w0, int h1,
+                                    int w1, int grad_mode, int64_t *out_n, int32_t *out_box4);
+
+/* step() followed by the Processor's scatter of the K solved pixels into the
+ * crop box (process.py:273-280): out_crop is uint8 [x1-x0, y1-y0, 3], holding
+ * the target's pixels outside the mask.  Only valid after
+ * fpie_b200_equ_reset_from_images. */
+int fpie_b200_equ_step_paste(fpie_b200_equ *e, int iters, uint8_t *out_crop, float *out_err3);
+/* Read back the system built by reset_from_images (parity checks). */
+int fpie_b200_equ_system(fpie_b200_equ *e, int32_t *out_A, float *out_X, float *out_B);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPIE_B200_H_ */

@@ -1,0 +1,203 @@
+"""EquSolver parity on the GPU, through the C ABI.
+
+Same tolerances as test_gpu_grid.py; the gather kernel uses numpy's add order
+((((B + X[up]) + X[down]) + X[left]) + X[right]) / 4, so states are required
+to be bit-exact against the oracle.
+"""
+
+import numpy as np
+import pytest
+from conftest import GOLDEN_CASES, MODES, golden_case
+
+from oracle import c_oracle, np_oracle
+
+pytestmark = pytest.mark.gpu
+
+ERR_RTOL = 1e-4
+
+
+def _solver(block=256):
+    import fpie_b200
+
+    return fpie_b200.EquSolver(block)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_partition_matches_numpy_core(golden, name):
+    s = _solver()
+    mask = golden[f"{name}/grid/max/mask_crop"]
+    ids = s.partition(mask)
+    assert ids.shape == mask.shape
+    np.testing.assert_array_equal(ids, np_oracle.partition_rowmajor(mask))
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 37), (64, 64), (63, 65), (300, 4099), (2048, 2051)])
+def test_partition_scan_sizes(shape):
+    rng = np.random.default_rng(shape[0] + shape[1])
+    mask = (rng.random(shape) < 0.6).astype(np.int32) * rng.integers(1, 5, shape).astype(np.int32)
+    s = _solver()
+    np.testing.assert_array_equal(s.partition(mask), np_oracle.partition_rowmajor(mask))
+    # non-contiguous view (fpie/process.py:224)
+    if shape[0] > 4 and shape[1] > 4:
+        view = mask[1:-2, 2:-1]
+        np.testing.assert_array_equal(s.partition(view), np_oracle.partition_rowmajor(view))
+    # negative entries count as unmasked (mask > 0, fpie/core/cuda/equ.cu:46)
+    neg = mask.copy()
+    neg[neg == 2] = -1
+    np.testing.assert_array_equal(s.partition(neg), np_oracle.partition_rowmajor(neg))
+
+
+@pytest.mark.parametrize("block", [32, 256, 1024])
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_core_matches_reference_golden(golden, name, block):
+    c = golden_case(golden, name)
+    s = _solver(block)
+    for mode in MODES:
+        key = f"{name}/equ/{mode}"
+        A, X, B = golden[f"{key}/A"], golden[f"{key}/X0"], golden[f"{key}/B"]
+        s.reset(A.shape[0], A, X, B)
+        for si, it in enumerate(c["steps"]):
+            img, err = s.step(it)
+            want = golden[f"{key}/state{si}"]
+            np.testing.assert_array_equal(s.state(), want)
+            np.testing.assert_array_equal(img, np_oracle.clip_u8(want))
+            assert img.shape == (A.shape[0], 3) and img.dtype == np.uint8 and err.dtype == np.float32
+            np.testing.assert_allclose(err, golden[f"{key}/err{si}"], rtol=ERR_RTOL, atol=1e-3)
+            np.testing.assert_allclose(err, np_oracle.equ_residual_f64(A, want, B), rtol=ERR_RTOL, atol=1e-3)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+@pytest.mark.parametrize("mode", MODES)
+def test_processor_matches_reference_golden(golden, name, mode):
+    """EquProcessor.reset on the device: scan + A/X/B build + paste."""
+    import fpie_b200
+
+    c = golden_case(golden, name)
+    proc = fpie_b200.EquProcessor(mode, "b200")
+    n = proc.reset(c["src"], c["mask"], c["tgt"], c["off_src"], c["off_tgt"])
+    key = f"{name}/equ/{mode}"
+    assert n == int(golden[f"{key}/n"])
+    A, X, B = proc.core.system()
+    np.testing.assert_array_equal(A, golden[f"{key}/A"])
+    np.testing.assert_array_equal(X, golden[f"{key}/X0"])
+    np.testing.assert_array_equal(B, golden[f"{key}/B"])
+    first = None
+    for si, it in enumerate(c["steps"]):
+        out, err = proc.step(it)
+        first = out if first is None else first
+        assert out is first
+        np.testing.assert_array_equal(out, golden[f"{key}/img{si}"])
+        np.testing.assert_array_equal(proc.core.state(), golden[f"{key}/state{si}"])
+        np.testing.assert_allclose(err, golden[f"{key}/err{si}"], rtol=ERR_RTOL, atol=1e-3)
+
+
+@pytest.mark.parametrize("kind,size", [("ring", 300), ("star", 511), ("holes", 257), ("circle", 1024), ("square", 640)])
+def test_synthetic_masks_vs_c_oracle(kind, size):
+    import fpie_b200
+    from fpie_b200 import synth
+
+    src, mask, tgt = synth.make_problem(kind, size, size + 3, seed=9)
+    mode = MODES[size % 3]
+    n, A, X, B, index = np_oracle.equ_system(src, mask, tgt, (0, 0), (0, 0), mode)
+    # core-level: oracle-built system through reset(N, A, X, B)
+    s = _solver()
+    s.reset(n, A, X, B)
+    img, err = s.step(60)
+    want = c_oracle.equ_sweeps(A, X, B, 60)
+    np.testing.assert_array_equal(s.state(), want)
+    np.testing.assert_array_equal(img, c_oracle.clip_u8(want))
+    e32, e64 = c_oracle.equ_residual(A, want, B)
+    np.testing.assert_allclose(err, e64, rtol=ERR_RTOL, atol=1e-3)
+    np.testing.assert_allclose(err, e32, rtol=1e-3, atol=1e-3)  # the oracle's sequential fp32 sum drifts by itself
+    # processor-level: device-built system is identical, pasted image too
+    proc = fpie_b200.EquProcessor(mode, "b200")
+    assert proc.reset(src, mask, tgt, (0, 0), (0, 0)) == n
+    A2, X2, B2 = proc.core.system()
+    np.testing.assert_array_equal(A2, A)
+    np.testing.assert_array_equal(X2, X)
+    np.testing.assert_array_equal(B2, B)
+    out, err2 = proc.step(60)
+    canvas = tgt.copy()
+    canvas[index] = c_oracle.clip_u8(want)[1:]
+    np.testing.assert_array_equal(out, canvas)
+    np.testing.assert_allclose(err2, e64, rtol=ERR_RTOL, atol=1e-3)
+
+
+def test_partition_through_reference_flow():
+    """The exact call sequence of EquProcessor.mask2index (process.py:180-190) with our partition."""
+    from fpie_b200 import synth
+
+    src, mask, tgt = synth.make_problem("star", 200, 240, seed=2)
+    m_full, (x0, x1, y0, y1) = np_oracle.canonical_mask(mask)
+    crop = m_full[x0:x1, y0:y1]  # non-contiguous view
+    s = _solver()
+    ids = s.partition(crop)
+    n, A, X, B, _ = np_oracle.equ_system(src, mask, tgt, (0, 0), (0, 0), "avg", ids=ids)
+    n2, A2, X2, B2, _ = np_oracle.equ_system(src, mask, tgt, (0, 0), (0, 0), "avg")
+    assert n == n2
+    np.testing.assert_array_equal(A, A2)
+    np.testing.assert_array_equal(B, B2)
+
+
+def test_step_calls_accumulate_and_reset_reuses_solver(golden):
+    s = _solver()
+    for name in ("ring_off", "holes_full"):
+        A, X, B = (golden[f"{name}/equ/max/{k}"] for k in ("A", "X0", "B"))
+        s.reset(A.shape[0], A, X, B)
+        s.step(5)
+        s.step(0)
+        s.step(8)
+        a = s.state()
+        s.reset(A.shape[0], A, X, B)
+        s.step(13)
+        np.testing.assert_array_equal(a, s.state())
+        np.testing.assert_array_equal(a, np_oracle.equ_sweeps(A, X, B, 13))
+
+
+def test_edge_and_error_behaviour():
+    import fpie_b200
+
+    s = _solver()
+    with pytest.raises(RuntimeError):
+        s.step(1)
+    # N = 1: only the constant row
+    s.reset(1, np.zeros((1, 4), np.int32), np.zeros((1, 3), np.float32), np.zeros((1, 3), np.float32))
+    img, err = s.step(3)
+    assert img.shape == (1, 3) and (img == 0).all() and (err == 0).all()
+    # out-of-range neighbour index is rejected (the reference would read out of bounds)
+    A = np.zeros((4, 4), np.int32)
+    A[2, 1] = 4
+    with pytest.raises(RuntimeError, match="outside"):
+        s.reset(4, A, np.zeros((4, 3), np.float32), np.zeros((4, 3), np.float32))
+    A[2, 1] = -1
+    with pytest.raises(RuntimeError, match="outside"):
+        s.reset(4, A, np.zeros((4, 3), np.float32), np.zeros((4, 3), np.float32))
+    with pytest.raises(ValueError):
+        s.reset(4, np.zeros((4, 3), np.int32), np.zeros((4, 3), np.float32), np.zeros((4, 3), np.float32))
+    p = fpie_b200.EquProcessor("src", "b200")
+    z = np.zeros((10, 10, 3), np.uint8)
+    with pytest.raises(RuntimeError, match="empty"):
+        p.reset(z, np.zeros((10, 10), np.uint8), z, (0, 0), (0, 0))
+    with pytest.raises(RuntimeError, match="outside the target"):
+        p.reset(z, np.full((10, 10), 255, np.uint8), z, (0, 0), (0, 5))
+    with pytest.raises(ValueError):
+        fpie_b200.EquProcessor("median", "b200")
+
+
+def test_large_irregular_mask():
+    """2048^2 ring (about 2.2 M unknowns), 40 sweeps, bit-exact vs the C restatement."""
+    import fpie_b200
+    from fpie_b200 import synth
+
+    src, mask, tgt = synth.make_problem("ring", 2048, 2048, seed=1)
+    proc = fpie_b200.EquProcessor("avg", "b200")
+    n = proc.reset(src, mask, tgt, (0, 0), (0, 0))
+    A, X, B = proc.core.system()
+    out, err = proc.step(40)
+    want = c_oracle.equ_sweeps(A, X, B, 40)
+    np.testing.assert_array_equal(proc.core.state(), want)
+    assert n == A.shape[0] and n > 2_000_000
+    np.testing.assert_allclose(err, c_oracle.equ_residual(A, want, B)[1], rtol=ERR_RTOL)
+    n0, A0, X0, B0, _ = np_oracle.equ_system(src, mask, tgt, (0, 0), (0, 0), "avg")
+    np.testing.assert_array_equal(A, A0)
+    np.testing.assert_array_equal(B, B0)
