@@ -210,39 +210,92 @@ grid_sweepk_kernel(PlaneGeom g, const uint32_t *__restrict__ bits, const float *
   }
 }
 
+// One row of the register tile: 4 pixels, neighbours left/right by shuffle.
+template <bool MIXED>
+__device__ __forceinline__ void row_update(float4 &xi, const float4 &hi, const float4 &prev, const float4 &nxt,
+                                           uint32_t nib) {
+  const float4 cur = xi;
+  const float lf = __shfl_up_sync(0xffffffffu, cur.w, 1);
+  const float rt = __shfl_down_sync(0xffffffffu, cur.x, 1);
+  float4 o;
+  o.x = jacobi_q(hi.x, prev.x, nxt.x, lf, cur.y);
+  o.y = jacobi_q(hi.y, prev.y, nxt.y, cur.x, cur.z);
+  o.z = jacobi_q(hi.z, prev.z, nxt.z, cur.y, cur.w);
+  o.w = jacobi_q(hi.w, prev.w, nxt.w, cur.z, rt);
+  if (MIXED) {
+    o.x = (nib & 1u) ? o.x : cur.x;
+    o.y = (nib & 2u) ? o.y : cur.y;
+    o.z = (nib & 4u) ? o.z : cur.z;
+    o.w = (nib & 8u) ? o.w : cur.w;
+  }
+  xi = o;
+}
+
+// One sweep of a register tile with a split-phase edge exchange: publish the
+// strip's first / last row, arrive on an mbarrier, update the R-2 interior rows
+// (they need no other warp), and only then wait for the neighbours' rows to
+// finish rows 0 and R-1.  The barrier latency hides behind (R-2)/R of the work.
+template <int R, int NW, bool MIXED>
+__device__ __forceinline__ void tile_sweep_split(float4 (&x)[R], const float4 (&h)[R],
+                                                 const uint32_t (&mb)[(R + 7) / 8], float4 (*mailbox)[2][NW][32],
+                                                 uint64_t *mail_bar, int parity, uint32_t &mphase) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  mailbox[parity][0][w][lane] = x[0];
+  mailbox[parity][1][w][lane] = x[R - 1];
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&mail_bar[parity]);
+  const float4 first_old = x[1];
+  float4 prev = x[0];
+#pragma unroll
+  for (int i = 1; i < R - 1; ++i) {
+    const float4 cur = x[i];
+    row_update<MIXED>(x[i], h[i], prev, x[i + 1], mb[i / 8] >> ((i % 8) * 4));
+    prev = cur;
+  }
+  mbar_wait(&mail_bar[parity], (mphase >> parity) & 1u);
+  mphase ^= 1u << parity;
+  const float4 up = (w > 0) ? mailbox[parity][1][w - 1][lane] : x[0];
+  const float4 dn = (w + 1 < NW) ? mailbox[parity][0][w + 1][lane] : x[R - 1];
+  row_update<MIXED>(x[0], h[0], up, first_old, mb[0]);
+  row_update<MIXED>(x[R - 1], h[R - 1], prev, dn, mb[(R - 1) / 8] >> (((R - 1) % 8) * 4));
+}
+
 // TMA-pipelined variant: while the CTA sweeps the tile it holds in registers,
 // the TMA engine streams the next tile (state + quarter-gradient, 2 x TH x 512 B)
 // into shared memory; one elected thread arms an mbarrier with the byte count
 // and issues two cp.async.bulk.tensor loads.  smem -> registers is a
-// conflict-free 128-bit copy (each warp reads one 512-byte row).
-template <int R, int NW>
-__global__ void __launch_bounds__(NW * 32, 1)
-grid_sweepk_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h,
-                       PlaneGeom g, const uint32_t *__restrict__ bits, float *__restrict__ xout,
-                       const int4 *__restrict__ tiles, int ntiles, int nsweeps, int halo_y, int halo_x) {
+// conflict-free 128-bit copy (each warp reads one 512-byte row).  OCC CTAs share
+// an SM so that one CTA's load / store phases overlap another's sweeps.
+template <int R, int NW, int OCC>
+__global__ void __launch_bounds__(NW * 32, OCC)
+grid_sweepk_pipe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h,
+                        PlaneGeom g, const uint32_t *__restrict__ bits, float *__restrict__ xout,
+                        const int4 *__restrict__ tiles, int ntiles, int nsweeps, int halo_y, int halo_x) {
   constexpr int TH = R * NW;
   constexpr uint32_t TILE_BYTES = TH * TILE_W * 4;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float *sx = reinterpret_cast<float *>(smem_raw);
   float *sh = sx + TH * TILE_W;
   float4(*mailbox)[2][NW][32] = reinterpret_cast<float4(*)[2][NW][32]>(sh + TH * TILE_W);
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bars[3];  // [0] TMA landing, [1..2] edge exchange per sweep parity
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 
   if (threadIdx.x == 0) {
-    mbar_init(&bar, 1);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], NW);
+    mbar_init(&bars[2], NW);
     mbar_fence_init();
   }
   __syncthreads();
   int t = blockIdx.x;
   if (threadIdx.x == 0 && t < ntiles) {
     const int4 td = tiles[t];
-    mbar_expect_tx(&bar, 2 * TILE_BYTES);
-    tma_load_3d(sx, &tm_x, td.y, td.x, td.z, &bar);
-    tma_load_3d(sh, &tm_h, td.y, td.x, td.z, &bar);
+    mbar_expect_tx(&bars[0], 2 * TILE_BYTES);
+    tma_load_3d(sx, &tm_x, td.y, td.x, td.z, &bars[0]);
+    tma_load_3d(sh, &tm_h, td.y, td.x, td.z, &bars[0]);
   }
   int parity = 0;
-  uint32_t phase = 0;
+  uint32_t phase = 0, mphase = 0;
   for (; t < ntiles; t += gridDim.x) {
     const int4 td = tiles[t];
     const int prow0 = td.x + w * R;
@@ -253,7 +306,7 @@ grid_sweepk_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     uint32_t mb[(R + 7) / 8];
     load_mask_bits<R>(mb, full, bits, g.wpitch, prow0, pcol);
 
-    mbar_wait(&bar, phase);
+    mbar_wait(&bars[0], phase);
     phase ^= 1;
     const int soff = (w * R) * TILE_W + 4 * lane;
 #pragma unroll
@@ -264,11 +317,27 @@ grid_sweepk_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     const int tn = t + gridDim.x;
     if (threadIdx.x == 0 && tn < ntiles) {
       const int4 nd = tiles[tn];
-      mbar_expect_tx(&bar, 2 * TILE_BYTES);
-      tma_load_3d(sx, &tm_x, nd.y, nd.x, nd.z, &bar);
-      tma_load_3d(sh, &tm_h, nd.y, nd.x, nd.z, &bar);
+      mbar_expect_tx(&bars[0], 2 * TILE_BYTES);
+      tma_load_3d(sx, &tm_x, nd.y, nd.x, nd.z, &bars[0]);
+      tma_load_3d(sh, &tm_h, nd.y, nd.x, nd.z, &bars[0]);
     }
-    tile_run<R, NW>(x, h, mb, full, mailbox, parity, nsweeps, halo_y, halo_x, xout + base, g.pitch);
+    for (int s = 0; s < nsweeps; ++s) {
+      if (full)
+        tile_sweep_split<R, NW, false>(x, h, mb, mailbox, &bars[1], parity, mphase);
+      else
+        tile_sweep_split<R, NW, true>(x, h, mb, mailbox, &bars[1], parity, mphase);
+      parity ^= 1;
+    }
+    // store the inner region; groups without masked pixels keep their constants
+    if ((4 * lane >= halo_x) && (4 * lane < TILE_W - halo_x)) {
+      float *out = xout + base;
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const int tr = w * R + i;
+        const uint32_t nib = (mb[i / 8] >> ((i % 8) * 4)) & 0xFu;
+        if (tr >= halo_y && tr < TH - halo_y && nib) st4(out + (long long)i * g.pitch, x[i]);
+      }
+    }
   }
 }
 
@@ -589,19 +658,19 @@ struct SweepArgs {
 
 template <int R, int NW>
 void launch_direct(const SweepArgs &a) {
-  grid_sweepk_kernel<R, NW><<<a.grid, NW * 32, 0, a.stream>>>(a.g, a.bits, a.xin, a.xout, a.hq, a.tiles, a.ntiles,
+  grid_sweepk_kernel<R, NW><<<std::min(a.ntiles, a.grid), NW * 32, 0, a.stream>>>(a.g, a.bits, a.xin, a.xout, a.hq, a.tiles, a.ntiles,
                                                               a.nsweeps, a.halo_y, a.halo_x);
 }
 
 template <int R, int NW>
-constexpr size_t tma_smem_bytes() {
+constexpr size_t pipe_smem_bytes() {
   return (size_t)2 * R * NW * TILE_W * 4 + sizeof(float4) * 2 * 2 * NW * 32;
 }
 
-template <int R, int NW>
-void launch_tma(const SweepArgs &a) {
-  auto kernel = grid_sweepk_tma_kernel<R, NW>;
-  constexpr size_t smem = tma_smem_bytes<R, NW>();
+template <int R, int NW, int OCC>
+void launch_pipe(const SweepArgs &a) {
+  auto kernel = grid_sweepk_pipe_kernel<R, NW, OCC>;
+  constexpr size_t smem = pipe_smem_bytes<R, NW>();
   static int configured_device = -1;  // the attribute is per function and per device
   int dev = 0;
   CUDA_CHECK(cudaGetDevice(&dev));
@@ -609,24 +678,42 @@ void launch_tma(const SweepArgs &a) {
     CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured_device = dev;
   }
-  kernel<<<a.grid, NW * 32, smem, a.stream>>>(*a.tm_x, *a.tm_h, a.g, a.bits, a.xout, a.tiles, a.ntiles, a.nsweeps,
-                                              a.halo_y, a.halo_x);
+  const int grid = std::min(a.ntiles, a.grid * OCC);
+  kernel<<<grid, NW * 32, smem, a.stream>>>(*a.tm_x, *a.tm_h, a.g, a.bits, a.xout, a.tiles, a.ntiles, a.nsweeps,
+                                            a.halo_y, a.halo_x);
+}
+
+struct VariantInfo {
+  int rows, warps, occ;
+  bool pipe;
+};
+
+// kernel variants (fpie_b200_grid_create `variant`): register-tile shape
+// rows/thread x warps, CTAs per SM; "pipe" = TMA-staged + split-phase exchange.
+VariantInfo variant_info(int v) {
+  switch (v) {
+    case 0: return {16, 6, 2, true};  // default
+    case 1: return {16, 12, 1, false};  // (tile shape unused: one sweep per launch)
+    case 2: return {16, 8, 1, false};
+    case 3: return {8, 16, 1, false};
+    case 4: return {16, 12, 1, false};
+    case 5: return {16, 12, 1, true};
+    case 6: return {14, 12, 1, true};
+    case 7: return {14, 6, 2, true};
+    case 8: return {12, 8, 2, true};
+    case 9: return {12, 14, 1, true};
+    case 10: return {10, 16, 1, true};
+    case 11: return {8, 16, 1, true};
+    case 12: return {8, 8, 2, true};
+    default: throw Error("fpie_b200: unknown grid kernel variant");
+  }
 }
 
 }  // namespace
 
-// kernel variants (fpie_b200_grid_create `variant`):
-//   0  TMA-pipelined, 16 rows/thread x 12 warps (tile 192 x 128)   [default]
-//   1  one sweep per launch
-//   2  direct loads, 16 x 8      3  direct loads, 8 x 16      4  direct loads, 16 x 12
-//   5  TMA-pipelined, 16 x 8     6  TMA-pipelined, 8 x 16
 TileShape GridSolver::shape_for(int variant) {
-  switch (variant) {
-    case 0: case 1: case 4: return {16, 12};
-    case 2: case 5: return {16, 8};
-    case 3: case 6: return {8, 16};
-    default: throw Error("fpie_b200: unknown grid kernel variant");
-  }
+  const VariantInfo v = variant_info(variant);
+  return {v.rows, v.warps};
 }
 
 void GridSolver::make_tensor_maps() {
@@ -654,7 +741,7 @@ void GridSolver::sweeps_async(int iters) {
     return;
   }
   SweepArgs a{};
-  a.grid = std::min(n_tile_entries_, sm_count_);
+  a.grid = sm_count_;
   a.stream = stream_;
   a.g = g;
   a.bits = bits_.ptr;
@@ -671,12 +758,18 @@ void GridSolver::sweeps_async(int iters) {
     a.xout = x_[cur_ ^ 1].ptr;
     a.tm_x = &tm_x_[cur_];
     switch (variant_) {
-      case 0: launch_tma<16, 12>(a); break;
+      case 0: launch_pipe<16, 6, 2>(a); break;
       case 2: launch_direct<16, 8>(a); break;
       case 3: launch_direct<8, 16>(a); break;
       case 4: launch_direct<16, 12>(a); break;
-      case 5: launch_tma<16, 8>(a); break;
-      case 6: launch_tma<8, 16>(a); break;
+      case 5: launch_pipe<16, 12, 1>(a); break;
+      case 6: launch_pipe<14, 12, 1>(a); break;
+      case 7: launch_pipe<14, 6, 2>(a); break;
+      case 8: launch_pipe<12, 8, 2>(a); break;
+      case 9: launch_pipe<12, 14, 1>(a); break;
+      case 10: launch_pipe<10, 16, 1>(a); break;
+      case 11: launch_pipe<8, 16, 1>(a); break;
+      case 12: launch_pipe<8, 8, 2>(a); break;
       default: throw Error("fpie_b200: unknown grid kernel variant");
     }
     cur_ ^= 1;
