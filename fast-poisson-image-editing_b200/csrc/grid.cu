@@ -184,21 +184,40 @@ __device__ __forceinline__ void load_mask_bits(uint32_t (&mb)[(R + 7) / 8], bool
   }
 }
 
+// Tile descriptors are packed into 8 bytes so that the two descriptors a CTA
+// keeps in flight cost four registers:  x = plane row | flags << 28,
+// y = plane col | plane << 20.
+__host__ __device__ __forceinline__ int2 pack_tile(int prow, int pcol, int plane, int flags) {
+  return make_int2(prow | (flags << 28), pcol | (plane << 20));
+}
+struct TileRef {
+  int prow, pcol, plane;
+  bool full;
+};
+__device__ __forceinline__ TileRef unpack_tile(int2 d) {
+  TileRef t;
+  t.prow = d.x & 0x0fffffff;
+  t.full = ((d.x >> 28) & 1) != 0;
+  t.pcol = d.y & 0xfffff;
+  t.plane = (d.y >> 20) & 0xfff;
+  return t;
+}
+
 // direct-load variant: registers are filled straight from global memory
 template <int R, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
 grid_sweepk_kernel(PlaneGeom g, const uint32_t *__restrict__ bits, const float *__restrict__ xin,
-                   float *__restrict__ xout, const float *__restrict__ hq, const int4 *__restrict__ tiles, int ntiles,
+                   float *__restrict__ xout, const float *__restrict__ hq, const int2 *__restrict__ tiles, int ntiles,
                    int nsweeps, int halo_y, int halo_x) {
   __shared__ float4 mailbox[2][2][NW][32];  // [sweep parity][0 = top row, 1 = bottom row][warp][lane]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int parity = 0;
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int4 td = tiles[t];  // x = plane row of tile origin, y = plane col, z = plane, w = flags (1 = fully masked)
-    const int prow0 = td.x + w * R;
-    const int pcol = td.y + 4 * lane;
-    const long long base = (long long)td.z * g.plane + (long long)prow0 * g.pitch + pcol;
-    const bool full = (td.w & 1) != 0;
+    const TileRef td = unpack_tile(tiles[t]);
+    const int prow0 = td.prow + w * R;
+    const int pcol = td.pcol + 4 * lane;
+    const long long base = (long long)td.plane * g.plane + (long long)prow0 * g.pitch + pcol;
+    const bool full = td.full;
     float4 x[R], h[R];
     uint32_t mb[(R + 7) / 8];
 #pragma unroll
@@ -261,22 +280,25 @@ __device__ __forceinline__ void tile_sweep_split(float4 (&x)[R], const float4 (&
 }
 
 // TMA-pipelined variant: while the CTA sweeps the tile it holds in registers,
-// the TMA engine streams the next tile (state + quarter-gradient, 2 x TH x 512 B)
-// into shared memory; one elected thread arms an mbarrier with the byte count
-// and issues two cp.async.bulk.tensor loads.  smem -> registers is a
-// conflict-free 128-bit copy (each warp reads one 512-byte row).  OCC CTAs share
-// an SM so that one CTA's load / store phases overlap another's sweeps.
+// the TMA engine streams the next tile (state, quarter-gradient and -- for
+// tiles that are not fully masked -- the mask words) into shared memory; one
+// elected thread arms an mbarrier with the byte count and issues the
+// cp.async.bulk.tensor loads.  smem -> registers is a conflict-free 128-bit
+// copy (each warp reads one 512-byte row).  Nothing at the top of the tile loop
+// depends on a global load: descriptors are fetched two tiles ahead.
 template <int R, int NW, int OCC>
 __global__ void __launch_bounds__(NW * 32, OCC)
 grid_sweepk_pipe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h,
-                        PlaneGeom g, const uint32_t *__restrict__ bits, float *__restrict__ xout,
-                        const int4 *__restrict__ tiles, int ntiles, int nsweeps, int halo_y, int halo_x) {
+                        const __grid_constant__ CUtensorMap tm_m, PlaneGeom g, float *__restrict__ xout,
+                        const int2 *__restrict__ tiles, int ntiles, int nsweeps, int halo_y, int halo_x) {
   constexpr int TH = R * NW;
   constexpr uint32_t TILE_BYTES = TH * TILE_W * 4;
+  constexpr uint32_t MASK_BYTES = TH * MASK_BOX_WORDS * 4;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float *sx = reinterpret_cast<float *>(smem_raw);
   float *sh = sx + TH * TILE_W;
-  float4(*mailbox)[2][NW][32] = reinterpret_cast<float4(*)[2][NW][32]>(sh + TH * TILE_W);
+  uint32_t *sm = reinterpret_cast<uint32_t *>(sh + TH * TILE_W);
+  float4(*mailbox)[2][NW][32] = reinterpret_cast<float4(*)[2][NW][32]>(sm + TH * MASK_BOX_WORDS);
   __shared__ uint64_t bars[3];  // [0] TMA landing, [1..2] edge exchange per sweep parity
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 
@@ -287,24 +309,32 @@ grid_sweepk_pipe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     mbar_fence_init();
   }
   __syncthreads();
+
+  auto issue = [&](int2 d) {  // one thread: arm the barrier and start the tile's bulk loads
+    const TileRef r = unpack_tile(d);
+    mbar_expect_tx(&bars[0], 2 * TILE_BYTES + (r.full ? 0u : MASK_BYTES));
+    tma_load_3d(sx, &tm_x, r.pcol, r.prow, r.plane, &bars[0]);
+    tma_load_3d(sh, &tm_h, r.pcol, r.prow, r.plane, &bars[0]);
+    // the bulk copy must start on a 16-byte boundary: round the word column down to a multiple of 4
+    if (!r.full) tma_load_2d(sm, &tm_m, (r.pcol >> 5) & ~3, r.prow, &bars[0]);
+  };
+
   int t = blockIdx.x;
-  if (threadIdx.x == 0 && t < ntiles) {
-    const int4 td = tiles[t];
-    mbar_expect_tx(&bars[0], 2 * TILE_BYTES);
-    tma_load_3d(sx, &tm_x, td.y, td.x, td.z, &bars[0]);
-    tma_load_3d(sh, &tm_h, td.y, td.x, td.z, &bars[0]);
-  }
+  if (t >= ntiles) return;
+  const int stride = gridDim.x;
+  int2 cur = tiles[t];
+  int2 nxt = (t + stride < ntiles) ? tiles[t + stride] : cur;
+  if (threadIdx.x == 0) issue(cur);
   int parity = 0;
   uint32_t phase = 0, mphase = 0;
-  for (; t < ntiles; t += gridDim.x) {
-    const int4 td = tiles[t];
-    const int prow0 = td.x + w * R;
-    const int pcol = td.y + 4 * lane;
-    const long long base = (long long)td.z * g.plane + (long long)prow0 * g.pitch + pcol;
-    const bool full = (td.w & 1) != 0;
+  for (; t < ntiles; t += stride) {
+    // descriptor of the tile after next: consumed one full iteration from now
+    const int2 nxt2 = (t + 2 * stride < ntiles) ? tiles[t + 2 * stride] : nxt;
+    const TileRef td = unpack_tile(cur);
+    const int pcol = td.pcol + 4 * lane;
+    const long long base = (long long)td.plane * g.plane + (long long)(td.prow + w * R) * g.pitch + pcol;
     float4 x[R], h[R];
     uint32_t mb[(R + 7) / 8];
-    load_mask_bits<R>(mb, full, bits, g.wpitch, prow0, pcol);
 
     mbar_wait(&bars[0], phase);
     phase ^= 1;
@@ -313,16 +343,20 @@ grid_sweepk_pipe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     for (int i = 0; i < R; ++i) x[i] = ld4(sx + soff + i * TILE_W);
 #pragma unroll
     for (int i = 0; i < R; ++i) h[i] = ld4(sh + soff + i * TILE_W);
-    __syncthreads();  // every thread has drained the staging buffers
-    const int tn = t + gridDim.x;
-    if (threadIdx.x == 0 && tn < ntiles) {
-      const int4 nd = tiles[tn];
-      mbar_expect_tx(&bars[0], 2 * TILE_BYTES);
-      tma_load_3d(sx, &tm_x, nd.y, nd.x, nd.z, &bars[0]);
-      tma_load_3d(sh, &tm_h, nd.y, nd.x, nd.z, &bars[0]);
+#pragma unroll
+    for (int i = 0; i < (R + 7) / 8; ++i) mb[i] = td.full ? 0xffffffffu : 0u;
+    if (!td.full) {
+      const uint32_t *mrow = sm + (w * R) * MASK_BOX_WORDS + ((pcol >> 5) - ((td.pcol >> 5) & ~3));
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+        mb[i / 8] |= ((mrow[i * MASK_BOX_WORDS] >> (pcol & 31)) & 0xFu) << ((i % 8) * 4);
     }
+    __syncthreads();  // every thread has drained the staging buffers
+    if (threadIdx.x == 0 && t + stride < ntiles) issue(nxt);
+
+#pragma unroll 2
     for (int s = 0; s < nsweeps; ++s) {
-      if (full)
+      if (td.full)
         tile_sweep_split<R, NW, false>(x, h, mb, mailbox, &bars[1], parity, mphase);
       else
         tile_sweep_split<R, NW, true>(x, h, mb, mailbox, &bars[1], parity, mphase);
@@ -338,6 +372,8 @@ grid_sweepk_pipe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         if (tr >= halo_y && tr < TH - halo_y && nib) st4(out + (long long)i * g.pitch, x[i]);
       }
     }
+    cur = nxt;
+    nxt = nxt2;
   }
 }
 
@@ -511,7 +547,8 @@ void GridSolver::layout(int n, int m) {
   g.m = m;
   g.padr = PAD_ROWS;
   g.padc = PAD_COLS;
-  g.pitch = (int)round_up(g.padc + (long long)tiles_x * step_x + halo_x_ + 4, 32);
+  // multiple of 128 floats: mask rows (pitch / 32 words) stay 16-byte aligned for TMA
+  g.pitch = (int)round_up(g.padc + (long long)tiles_x * step_x + halo_x_ + 4, 128);
   g.rows = g.padr + tiles_y * step_y + block_k_ + 1;
   g.wpitch = g.pitch / 32;
   g.groups = (int)ceil_div(m, 4);
@@ -620,7 +657,7 @@ void GridSolver::build_tiles() {
   std::vector<uint32_t> flags(ntiles);
   CUDA_CHECK(cudaMemcpyAsync(flags.data(), tile_flags_.ptr, ntiles * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));
-  std::vector<int4> list;
+  std::vector<int2> list;
   list.reserve((size_t)ntiles * 3);
   int64_t active = 0;
   for (int t = 0; t < ntiles; ++t) {
@@ -628,7 +665,7 @@ void GridSolver::build_tiles() {
     ++active;
     const int ty = t / tiles_x, tx = t % tiles_x;
     for (int ch = 0; ch < 3; ++ch)
-      list.push_back(make_int4(g.padr + ty * step_y - block_k_, g.padc + tx * step_x - halo_x_, ch,
+      list.push_back(pack_tile(g.padr + ty * step_y - block_k_, g.padc + tx * step_x - halo_x_, ch,
                                (flags[t] & 2u) ? 1 : 0));
   }
   stats_.active_tiles = active;
@@ -636,7 +673,7 @@ void GridSolver::build_tiles() {
   n_tile_entries_ = (int)list.size();
   tiles_.resize(std::max<size_t>(list.size(), 1));
   if (!list.empty())
-    CUDA_CHECK(cudaMemcpyAsync(tiles_.ptr, list.data(), list.size() * sizeof(int4), cudaMemcpyHostToDevice, stream_));
+    CUDA_CHECK(cudaMemcpyAsync(tiles_.ptr, list.data(), list.size() * sizeof(int2), cudaMemcpyHostToDevice, stream_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));
 }
 
@@ -652,7 +689,8 @@ struct SweepArgs {
   const float *hq;
   const CUtensorMap *tm_x;
   const CUtensorMap *tm_h;
-  const int4 *tiles;
+  const int2 *tiles;
+  const CUtensorMap *tm_m;
   int ntiles, nsweeps, halo_y, halo_x;
 };
 
@@ -664,7 +702,7 @@ void launch_direct(const SweepArgs &a) {
 
 template <int R, int NW>
 constexpr size_t pipe_smem_bytes() {
-  return (size_t)2 * R * NW * TILE_W * 4 + sizeof(float4) * 2 * 2 * NW * 32;
+  return (size_t)2 * R * NW * TILE_W * 4 + (size_t)R * NW * MASK_BOX_WORDS * 4 + sizeof(float4) * 2 * 2 * NW * 32;
 }
 
 template <int R, int NW, int OCC>
@@ -679,7 +717,7 @@ void launch_pipe(const SweepArgs &a) {
     configured_device = dev;
   }
   const int grid = std::min(a.ntiles, a.grid * OCC);
-  kernel<<<grid, NW * 32, smem, a.stream>>>(*a.tm_x, *a.tm_h, a.g, a.bits, a.xout, a.tiles, a.ntiles, a.nsweeps,
+  kernel<<<grid, NW * 32, smem, a.stream>>>(*a.tm_x, *a.tm_h, *a.tm_m, a.g, a.xout, a.tiles, a.ntiles, a.nsweeps,
                                             a.halo_y, a.halo_x);
 }
 
@@ -692,13 +730,13 @@ struct VariantInfo {
 // rows/thread x warps, CTAs per SM; "pipe" = TMA-staged + split-phase exchange.
 VariantInfo variant_info(int v) {
   switch (v) {
-    case 0: return {16, 6, 2, true};  // default
+    case 0: return {14, 12, 1, true};  // default
     case 1: return {16, 12, 1, false};  // (tile shape unused: one sweep per launch)
     case 2: return {16, 8, 1, false};
     case 3: return {8, 16, 1, false};
     case 4: return {16, 12, 1, false};
     case 5: return {16, 12, 1, true};
-    case 6: return {14, 12, 1, true};
+    case 6: return {16, 6, 2, true};
     case 7: return {14, 6, 2, true};
     case 8: return {12, 8, 2, true};
     case 9: return {12, 14, 1, true};
@@ -721,6 +759,7 @@ void GridSolver::make_tensor_maps() {
   for (int i = 0; i < 2; ++i)
     tm_x_[i] = make_plane_tensor_map(x_[i].ptr, g.pitch, g.rows, 3, g.plane, TILE_W, shape_.tile_h());
   tm_h_ = make_plane_tensor_map(hq_.ptr, g.pitch, g.rows, 3, g.plane, TILE_W, shape_.tile_h());
+  tm_m_ = make_mask_tensor_map(bits_.ptr, g.wpitch, g.rows, MASK_BOX_WORDS, shape_.tile_h());
 }
 
 void GridSolver::sweeps_async(int iters) {
@@ -747,6 +786,7 @@ void GridSolver::sweeps_async(int iters) {
   a.bits = bits_.ptr;
   a.hq = hq_.ptr;
   a.tm_h = &tm_h_;
+  a.tm_m = &tm_m_;
   a.tiles = tiles_.ptr;
   a.ntiles = n_tile_entries_;
   a.halo_y = block_k_;
@@ -758,12 +798,12 @@ void GridSolver::sweeps_async(int iters) {
     a.xout = x_[cur_ ^ 1].ptr;
     a.tm_x = &tm_x_[cur_];
     switch (variant_) {
-      case 0: launch_pipe<16, 6, 2>(a); break;
+      case 0: launch_pipe<14, 12, 1>(a); break;
       case 2: launch_direct<16, 8>(a); break;
       case 3: launch_direct<8, 16>(a); break;
       case 4: launch_direct<16, 12>(a); break;
       case 5: launch_pipe<16, 12, 1>(a); break;
-      case 6: launch_pipe<14, 12, 1>(a); break;
+      case 6: launch_pipe<16, 6, 2>(a); break;
       case 7: launch_pipe<14, 6, 2>(a); break;
       case 8: launch_pipe<12, 8, 2>(a); break;
       case 9: launch_pipe<12, 14, 1>(a); break;

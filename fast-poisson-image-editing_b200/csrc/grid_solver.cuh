@@ -16,6 +16,7 @@ namespace fpie {
 constexpr int TILE_W = 128;  // 32 lanes x float4
 constexpr int MAX_BLOCK_K = 16;
 constexpr int PAD_ROWS = 16;  // >= MAX_BLOCK_K
+constexpr int MASK_BOX_WORDS = 8;  // mask words staged per tile row (a 128-px row spans <= 5)
 constexpr int PAD_COLS = 32;  // >= round_up(MAX_BLOCK_K, 4), multiple of 32
 
 struct TileShape {
@@ -83,10 +84,11 @@ class GridSolver {
   DeviceBuffer<int32_t> mask_stage_;
   DeviceBuffer<uint8_t> img_;
   DeviceBuffer<double> err_;  // [3] residual sums + [1] unknown count (as double)
-  DeviceBuffer<int4> tiles_;
+  DeviceBuffer<int2> tiles_;
   DeviceBuffer<uint32_t> tile_flags_;
   CUtensorMap tm_x_[2];
   CUtensorMap tm_h_;
+  CUtensorMap tm_m_;
   int n_tile_entries_ = 0;
   double *host_err_ = nullptr;  // pinned [4]
   GridStats stats_;

@@ -37,6 +37,28 @@ inline CUtensorMap make_plane_tensor_map(const float *base, int pitch, int rows,
   return map;
 }
 
+// 2-D uint32 tensor map over the mask words [rows][wpitch], box [box_rows][box_words].
+inline CUtensorMap make_mask_tensor_map(const uint32_t *base, int wpitch, int rows, int box_words, int box_rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                               const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  FPIE_REQUIRE(fn && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+  CUtensorMap map;
+  const cuuint64_t dims[2] = {(cuuint64_t)wpitch, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)wpitch * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)box_words, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult rc = reinterpret_cast<EncodeFn>(fn)(
+      &map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t *>(base), dims, strides, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FPIE_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled (mask) failed");
+  return map;
+}
+
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -75,6 +97,14 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
       ::"r"(smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
 #endif
