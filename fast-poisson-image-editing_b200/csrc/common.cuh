@@ -84,6 +84,17 @@ struct PlaneGeom {
 #ifdef __CUDACC__
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+// predicated (branch-free) 128-bit global store
+__device__ __forceinline__ void st4_if(void *p, float4 v, uint32_t on) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.u32 p, %5, 0;\n"
+      "@p st.global.v4.f32 [%0], {%1, %2, %3, %4};\n"
+      "}\n" ::"l"(p),
+      "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(on)
+      : "memory");
+}
 
 // One Jacobi update in the reference's add order, evaluated on quarter-scaled
 // operands:  ((((g + U) + D) + L) + R) / 4  ==  fma(R,q, fma(L,q, fma(D,q, fma(U,q, g/4))))

@@ -10,6 +10,8 @@
 //   * tiles without masked pixels are never scheduled, fully masked tiles run
 //     a select-free instruction stream.
 
+#include <cuda_fp16.h>
+
 #include <algorithm>
 #include <cstring>
 
@@ -59,6 +61,20 @@ __global__ void aos_to_planes_kernel(PlaneGeom g, const float *__restrict__ aos,
     dst0[ch * g.plane + off] = v;
     if (dst1) dst1[ch * g.plane + off] = v;
   }
+}
+
+// fp32 quarter-gradient planes -> fp16 copy for the temporally blocked kernel.
+// *inexact is raised if any value does not survive the round trip (then the
+// fp32 planes are streamed instead).  Gradients built from uint8 images are
+// multiples of 1/8 below 256 and always survive.
+__global__ void planes_to_half_kernel(long long count, const float *__restrict__ src, __half *__restrict__ dst,
+                                      int *__restrict__ inexact) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const float v = src[i];
+  const __half h = __float2half_rn(v);
+  dst[i] = h;
+  if (!(__half2float(h) == v)) atomicOr(inexact, 1);
 }
 
 __global__ void planes_to_aos_kernel(PlaneGeom g, const float *__restrict__ src, float *__restrict__ aos) {
@@ -279,6 +295,22 @@ __device__ __forceinline__ void tile_sweep_split(float4 (&x)[R], const float4 (&
   row_update<MIXED>(x[R - 1], h[R - 1], prev, dn, mb[(R - 1) / 8] >> (((R - 1) % 8) * 4));
 }
 
+// Shared-memory layout of the pipelined kernel (all sections 128-byte aligned).
+template <int R, int NW, bool H16>
+struct PipeSmem {
+  static constexpr uint32_t align128(uint32_t v) { return (v + 127u) & ~127u; }
+  static constexpr int TH = R * NW;
+  static constexpr int H16_W = TILE_W + 8;  // fp16 box: start rounded down to 8 columns, 8 columns wider
+  static constexpr uint32_t X_BYTES = TH * TILE_W * 4;
+  static constexpr uint32_t H_BYTES = H16 ? TH * H16_W * 2 : X_BYTES;
+  static constexpr uint32_t M_BYTES = TH * MASK_BOX_WORDS * 4;
+  static constexpr uint32_t X_OFF = 0;
+  static constexpr uint32_t H_OFF = align128(X_OFF + X_BYTES);
+  static constexpr uint32_t M_OFF = align128(H_OFF + H_BYTES);
+  static constexpr uint32_t MAIL_OFF = align128(M_OFF + M_BYTES);
+  static constexpr uint32_t TOTAL = MAIL_OFF + 2 * 2 * NW * 32 * 16;
+};
+
 // TMA-pipelined variant: while the CTA sweeps the tile it holds in registers,
 // the TMA engine streams the next tile (state, quarter-gradient and -- for
 // tiles that are not fully masked -- the mask words) into shared memory; one
@@ -286,19 +318,20 @@ __device__ __forceinline__ void tile_sweep_split(float4 (&x)[R], const float4 (&
 // cp.async.bulk.tensor loads.  smem -> registers is a conflict-free 128-bit
 // copy (each warp reads one 512-byte row).  Nothing at the top of the tile loop
 // depends on a global load: descriptors are fetched two tiles ahead.
-template <int R, int NW, int OCC>
+template <int R, int NW, int OCC, bool H16>
 __global__ void __launch_bounds__(NW * 32, OCC)
 grid_sweepk_pipe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h,
                         const __grid_constant__ CUtensorMap tm_m, PlaneGeom g, float *__restrict__ xout,
                         const int2 *__restrict__ tiles, int ntiles, int nsweeps, int halo_y, int halo_x) {
   constexpr int TH = R * NW;
-  constexpr uint32_t TILE_BYTES = TH * TILE_W * 4;
-  constexpr uint32_t MASK_BYTES = TH * MASK_BOX_WORDS * 4;
+  using L = PipeSmem<R, NW, H16>;
+  constexpr int H16_W = L::H16_W;
+  constexpr uint32_t TILE_BYTES = L::X_BYTES, H_BYTES = L::H_BYTES, MASK_BYTES = L::M_BYTES;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  float *sx = reinterpret_cast<float *>(smem_raw);
-  float *sh = sx + TH * TILE_W;
-  uint32_t *sm = reinterpret_cast<uint32_t *>(sh + TH * TILE_W);
-  float4(*mailbox)[2][NW][32] = reinterpret_cast<float4(*)[2][NW][32]>(sm + TH * MASK_BOX_WORDS);
+  float *sx = reinterpret_cast<float *>(smem_raw + L::X_OFF);
+  unsigned char *sh = smem_raw + L::H_OFF;
+  uint32_t *sm = reinterpret_cast<uint32_t *>(smem_raw + L::M_OFF);
+  float4(*mailbox)[2][NW][32] = reinterpret_cast<float4(*)[2][NW][32]>(smem_raw + L::MAIL_OFF);
   __shared__ uint64_t bars[3];  // [0] TMA landing, [1..2] edge exchange per sweep parity
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 
@@ -312,9 +345,9 @@ grid_sweepk_pipe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
 
   auto issue = [&](int2 d) {  // one thread: arm the barrier and start the tile's bulk loads
     const TileRef r = unpack_tile(d);
-    mbar_expect_tx(&bars[0], 2 * TILE_BYTES + (r.full ? 0u : MASK_BYTES));
+    mbar_expect_tx(&bars[0], TILE_BYTES + H_BYTES + (r.full ? 0u : MASK_BYTES));
     tma_load_3d(sx, &tm_x, r.pcol, r.prow, r.plane, &bars[0]);
-    tma_load_3d(sh, &tm_h, r.pcol, r.prow, r.plane, &bars[0]);
+    tma_load_3d(sh, &tm_h, H16 ? (r.pcol & ~7) : r.pcol, r.prow, r.plane, &bars[0]);
     // the bulk copy must start on a 16-byte boundary: round the word column down to a multiple of 4
     if (!r.full) tma_load_2d(sm, &tm_m, (r.pcol >> 5) & ~3, r.prow, &bars[0]);
   };
@@ -341,8 +374,20 @@ grid_sweepk_pipe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     const int soff = (w * R) * TILE_W + 4 * lane;
 #pragma unroll
     for (int i = 0; i < R; ++i) x[i] = ld4(sx + soff + i * TILE_W);
+    if (H16) {
+      const __half *hrow = reinterpret_cast<const __half *>(sh) + (w * R) * H16_W + (td.pcol & 7) + 4 * lane;
 #pragma unroll
-    for (int i = 0; i < R; ++i) h[i] = ld4(sh + soff + i * TILE_W);
+      for (int i = 0; i < R; ++i) {
+        const uint2 raw = *reinterpret_cast<const uint2 *>(hrow + i * H16_W);
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+        const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+        h[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+      }
+    } else {
+      const float *hrow = reinterpret_cast<const float *>(sh) + soff;
+#pragma unroll
+      for (int i = 0; i < R; ++i) h[i] = ld4(hrow + i * TILE_W);
+    }
 #pragma unroll
     for (int i = 0; i < (R + 7) / 8; ++i) mb[i] = td.full ? 0xffffffffu : 0u;
     if (!td.full) {
@@ -362,14 +407,19 @@ grid_sweepk_pipe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         tile_sweep_split<R, NW, true>(x, h, mb, mailbox, &bars[1], parity, mphase);
       parity ^= 1;
     }
-    // store the inner region; groups without masked pixels keep their constants
-    if ((4 * lane >= halo_x) && (4 * lane < TILE_W - halo_x)) {
+    // store the inner region; groups without masked pixels keep their constants.
+    // Branch-free: one row-validity bitmask per thread, predicated 128-bit stores.
+    {
+      const int lo = max(halo_y - w * R, 0), hi = min(TH - halo_y - w * R, R);
+      uint32_t rows_ok = (hi > lo) ? ((1u << hi) - 1u) & ~((1u << lo) - 1u) : 0u;
+      if ((4 * lane < halo_x) || (4 * lane >= TILE_W - halo_x)) rows_ok = 0u;
       float *out = xout + base;
+      const uint32_t pitch_bytes = (uint32_t)g.pitch * 4u;
 #pragma unroll
       for (int i = 0; i < R; ++i) {
-        const int tr = w * R + i;
-        const uint32_t nib = (mb[i / 8] >> ((i % 8) * 4)) & 0xFu;
-        if (tr >= halo_y && tr < TH - halo_y && nib) st4(out + (long long)i * g.pitch, x[i]);
+        const uint32_t nib = td.full ? 1u : (mb[i / 8] >> ((i % 8) * 4)) & 0xFu;
+        const uint32_t on = ((rows_ok >> i) & 1u) && nib;
+        st4_if(reinterpret_cast<char *>(out) + (size_t)i * pitch_bytes, x[i], on);
       }
     }
     cur = nxt;
@@ -521,6 +571,10 @@ GridSolver::GridSolver(int device, cudaStream_t stream, int block_k, int variant
   CUDA_CHECK(cudaGetDeviceProperties(&prop, device_));
   FPIE_REQUIRE(prop.major >= 10, "fpie_b200 is built for sm_100a (Blackwell) only");
   sm_count_ = prop.multiProcessorCount;
+  if (variant_ >= 100) {  // 100 + v: variant v, always streaming the fp32 gradient planes
+    force_h32_ = true;
+    variant_ -= 100;
+  }
   if (block_k <= 0) block_k = 8;
   FPIE_REQUIRE(block_k <= MAX_BLOCK_K, "block_k must be in 1..16");
   block_k_ = block_k;
@@ -632,6 +686,20 @@ void GridSolver::reset_from_images(const uint8_t *src, int sh, int sw, const uin
 }
 
 void GridSolver::after_state_loaded() {
+  // fp16 copy of the quarter-gradient (halves that stream when every value is exactly representable)
+  {
+    const long long count = geom_.plane * 3;
+    hq16_.resize((size_t)count);
+    flag_.resize(1);
+    CUDA_CHECK(cudaMemsetAsync(flag_.ptr, 0, sizeof(int), stream_));
+    planes_to_half_kernel<<<blocks_for(count, 256), 256, 0, stream_>>>(count, hq_.ptr, hq16_.ptr, flag_.ptr);
+    CUDA_CHECK(cudaGetLastError());
+    stats_.launches += 1;
+    int inexact = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&inexact, flag_.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    h16_ok_ = (inexact == 0) && !force_h32_;
+  }
   make_tensor_maps();
   // unknown count (stored as a 64-bit integer in err_[3])
   CUDA_CHECK(cudaMemcpyAsync(host_err_ + 3, err_.ptr + 3, sizeof(double), cudaMemcpyDeviceToHost, stream_));
@@ -691,6 +759,7 @@ struct SweepArgs {
   const CUtensorMap *tm_h;
   const int2 *tiles;
   const CUtensorMap *tm_m;
+  bool h16;
   int ntiles, nsweeps, halo_y, halo_x;
 };
 
@@ -700,15 +769,10 @@ void launch_direct(const SweepArgs &a) {
                                                               a.nsweeps, a.halo_y, a.halo_x);
 }
 
-template <int R, int NW>
-constexpr size_t pipe_smem_bytes() {
-  return (size_t)2 * R * NW * TILE_W * 4 + (size_t)R * NW * MASK_BOX_WORDS * 4 + sizeof(float4) * 2 * 2 * NW * 32;
-}
-
-template <int R, int NW, int OCC>
-void launch_pipe(const SweepArgs &a) {
-  auto kernel = grid_sweepk_pipe_kernel<R, NW, OCC>;
-  constexpr size_t smem = pipe_smem_bytes<R, NW>();
+template <int R, int NW, int OCC, bool H16>
+void launch_pipe_h(const SweepArgs &a) {
+  auto kernel = grid_sweepk_pipe_kernel<R, NW, OCC, H16>;
+  constexpr size_t smem = PipeSmem<R, NW, H16>::TOTAL;
   static int configured_device = -1;  // the attribute is per function and per device
   int dev = 0;
   CUDA_CHECK(cudaGetDevice(&dev));
@@ -719,6 +783,14 @@ void launch_pipe(const SweepArgs &a) {
   const int grid = std::min(a.ntiles, a.grid * OCC);
   kernel<<<grid, NW * 32, smem, a.stream>>>(*a.tm_x, *a.tm_h, *a.tm_m, a.g, a.xout, a.tiles, a.ntiles, a.nsweeps,
                                             a.halo_y, a.halo_x);
+}
+
+template <int R, int NW, int OCC>
+void launch_pipe(const SweepArgs &a) {
+  if (a.h16)
+    launch_pipe_h<R, NW, OCC, true>(a);
+  else
+    launch_pipe_h<R, NW, OCC, false>(a);
 }
 
 struct VariantInfo {
@@ -743,6 +815,10 @@ VariantInfo variant_info(int v) {
     case 10: return {10, 16, 1, true};
     case 11: return {8, 16, 1, true};
     case 12: return {8, 8, 2, true};
+    case 13: return {7, 24, 1, true};
+    case 14: return {7, 12, 2, true};
+    case 15: return {6, 24, 1, true};
+    case 16: return {6, 28, 1, true};
     default: throw Error("fpie_b200: unknown grid kernel variant");
   }
 }
@@ -759,6 +835,7 @@ void GridSolver::make_tensor_maps() {
   for (int i = 0; i < 2; ++i)
     tm_x_[i] = make_plane_tensor_map(x_[i].ptr, g.pitch, g.rows, 3, g.plane, TILE_W, shape_.tile_h());
   tm_h_ = make_plane_tensor_map(hq_.ptr, g.pitch, g.rows, 3, g.plane, TILE_W, shape_.tile_h());
+  tm_h16_ = make_plane_tensor_map(hq16_.ptr, g.pitch, g.rows, 3, g.plane, TILE_W + 8, shape_.tile_h(), true);
   tm_m_ = make_mask_tensor_map(bits_.ptr, g.wpitch, g.rows, MASK_BOX_WORDS, shape_.tile_h());
 }
 
@@ -785,7 +862,8 @@ void GridSolver::sweeps_async(int iters) {
   a.g = g;
   a.bits = bits_.ptr;
   a.hq = hq_.ptr;
-  a.tm_h = &tm_h_;
+  a.h16 = h16_ok_;
+  a.tm_h = h16_ok_ ? &tm_h16_ : &tm_h_;
   a.tm_m = &tm_m_;
   a.tiles = tiles_.ptr;
   a.ntiles = n_tile_entries_;
@@ -810,6 +888,10 @@ void GridSolver::sweeps_async(int iters) {
       case 10: launch_pipe<10, 16, 1>(a); break;
       case 11: launch_pipe<8, 16, 1>(a); break;
       case 12: launch_pipe<8, 8, 2>(a); break;
+      case 13: launch_pipe<7, 24, 1>(a); break;
+      case 14: launch_pipe<7, 12, 2>(a); break;
+      case 15: launch_pipe<6, 24, 1>(a); break;
+      case 16: launch_pipe<6, 28, 1>(a); break;
       default: throw Error("fpie_b200: unknown grid kernel variant");
     }
     cur_ ^= 1;

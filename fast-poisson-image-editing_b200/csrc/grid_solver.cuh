@@ -5,6 +5,7 @@
 #include <vector>
 
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -79,6 +80,10 @@ class GridSolver {
   int win_lo_ = 0, win_hi_ = 0;
   DeviceBuffer<float> x_[2];
   DeviceBuffer<float> hq_;
+  DeviceBuffer<__half> hq16_;
+  DeviceBuffer<int> flag_;
+  bool h16_ok_ = false;
+  bool force_h32_ = false;
   DeviceBuffer<uint32_t> bits_;
   DeviceBuffer<float> stage_;
   DeviceBuffer<int32_t> mask_stage_;
@@ -88,6 +93,7 @@ class GridSolver {
   DeviceBuffer<uint32_t> tile_flags_;
   CUtensorMap tm_x_[2];
   CUtensorMap tm_h_;
+  CUtensorMap tm_h16_;
   CUtensorMap tm_m_;
   int n_tile_entries_ = 0;
   double *host_err_ = nullptr;  // pinned [4]

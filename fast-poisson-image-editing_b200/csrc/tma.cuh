@@ -11,8 +11,8 @@ namespace fpie {
 
 // Encode a 3-D fp32 tensor map over [planes][rows][pitch] with a box of
 // [1][box_rows][box_cols] elements, no swizzle, zero fill outside the tensor.
-inline CUtensorMap make_plane_tensor_map(const float *base, int pitch, int rows, int planes, long long plane_stride,
-                                         int box_cols, int box_rows) {
+inline CUtensorMap make_plane_tensor_map(const void *base, int pitch, int rows, int planes, long long plane_stride,
+                                         int box_cols, int box_rows, bool half = false) {
   typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -26,11 +26,13 @@ inline CUtensorMap make_plane_tensor_map(const float *base, int pitch, int rows,
   }
   CUtensorMap map;
   const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)planes};
-  const cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)plane_stride * 4};
+  const cuuint64_t esize = half ? 2 : 4;
+  const cuuint64_t strides[2] = {(cuuint64_t)pitch * esize, (cuuint64_t)plane_stride * esize};
   const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult rc =
-      encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, estr,
+      encode(&map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+             const_cast<void *>(base), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FPIE_REQUIRE(rc == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");

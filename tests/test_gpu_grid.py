@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 STATE_TOL = 1e-3
 ERR_RTOL = 1e-4
 
-VARIANTS = [(0, 0), (0, 1), (0, 3), (0, 16), (1, 0), (2, 8), (3, 3), (4, 2), (5, 6), (6, 7), (7, 5), (8, 4), (9, 12),
+VARIANTS = [(100, 0), (105, 5), (0, 0), (0, 1), (0, 3), (0, 16), (1, 0), (2, 8), (3, 3), (4, 2), (5, 6), (6, 7), (7, 5), (8, 4), (9, 12),
             (10, 9), (11, 8), (12, 2)]  # (variant, block_k)
 
 
@@ -108,6 +108,21 @@ def test_random_grids_bitexact_vs_c_oracle(shape, iters, variant, block_k):
     e32, e64 = c_oracle.grid_residual(mask, want, grad)
     _check_err(err, e64, e32, terms=int(mask.sum()))
     assert s.info()["unknowns"] == int(mask.sum())
+
+
+@pytest.mark.parametrize("variant", [0, 100, 107, 4, 1])
+def test_arbitrary_float_gradients(variant):
+    """Core-level grads need not be multiples of 1/2 (the Processor's are): values
+    that do not survive fp16 must take the fp32 streaming path and stay bit-exact;
+    variant 100+v forces that path for fp16-exact inputs too."""
+    rng = np.random.default_rng(21)
+    mask, tgt, grad = _random_grid(200, 333, seed=4)
+    s = _solver(variant, 8)
+    for g in (grad, (rng.standard_normal(grad.shape) * 37.7).astype(np.float32) * (mask[..., None] != 0)):
+        t = (tgt + rng.random(tgt.shape).astype(np.float32)).astype(np.float32)
+        s.reset(mask.size, mask, t, g)
+        s.step(29)
+        np.testing.assert_array_equal(s.state(), c_oracle.grid_sweeps(mask, t, g, 29))
 
 
 def test_step_calls_accumulate_and_reset_reuses_solver():
