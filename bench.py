@@ -204,7 +204,7 @@ def run_reference(args, work, name):
 
     size = work["size"]
     if name == "cfg4":
-        size = 16384  # int32 offsets in the reference overflow at 3*N*M >= 2^31 (base_solver.h:114-117)
+        size = 8192  # the reference overflows int32 offsets at 3*N*M >= 2^31 (base_solver.h:114-117); 8192^2 keeps the host-side numpy setup to about a minute, throughput per pixel is size-independent
     src, mask, tgt = synth.make_problem(work["mask"], size, size, seed=0)
     w = dict(work, size=size)
     total = args.steps + args.warmup
@@ -245,7 +245,7 @@ def run_single(args, work, name):
 
     dev = 0
     torch.cuda.set_device(dev)
-    size, iters = work["size"], (args.iters or work["iters"])
+    size, iters = (args.size or work["size"]), (args.iters or work["iters"])
     src, mask, tgt = synth.make_problem(work["mask"], size, size, seed=0)
     is_grid = work["solver"] == "grid"
     Proc = fpie_b200.GridProcessor if is_grid else fpie_b200.EquProcessor
@@ -366,6 +366,148 @@ def run_single(args, work, name):
     print(json.dumps(line))
 
 
+def slab_images(work, plan, n, m, rank):
+    """Synthetic uint8 slab (rows plan.slab_lo:plan.slab_hi of an n x m blend)."""
+    from fpie_b200 import synth
+
+    rows = plan.slab_rows
+    rng = np.random.default_rng(1000 + rank)
+    src = np.empty((rows, m, 3), np.uint8)
+    tgt = np.empty((rows, m, 3), np.uint8)
+    for img in (src, tgt):
+        for r in range(0, rows, 2048):
+            img[r : r + 2048] = rng.integers(0, 256, size=(min(2048, rows - r), m, 3), dtype=np.uint8)
+    if work["mask"] == "square":
+        mask = np.full((rows, m), 255, np.uint8)
+        unknowns = (n - 2) * (m - 2)
+    else:
+        full = synth.make_mask(work["mask"], n, m)
+        full[0] = full[-1] = 0
+        full[:, 0] = full[:, -1] = 0
+        mask = np.ascontiguousarray(full[plan.slab_lo : plan.slab_hi])
+        unknowns = int((full > 127).sum())
+    return src, mask, tgt, unknowns
+
+
+def run_band(args, work, name):
+    """N > 1: the grid is cut into row bands, one process per GPU, deep halos over NCCL."""
+    import torch
+
+    import fpie_b200
+    from fpie_b200 import band
+
+    dist = band.init_process_group_from_env("nccl")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(dev)
+    n = m = args.size or work["size"]
+    iters = args.iters or work["iters"]
+    halo = args.halo
+    plan = band.make_plan(n, world, rank, halo)
+    src, mask, tgt, unknowns = slab_images(work, plan, n, m, rank)
+    core = fpie_b200.GridSolver(8, 8, device=dev, block_k=args.block_k)
+    solver = band.BandGridSolver(band.CudaBandCore(core), dist, halo=halo)
+    t0 = time.perf_counter()
+    solver.reset_slab(n, src, mask, tgt, work["grad"])
+    torch.cuda.synchronize()
+    reset_s = time.perf_counter() - t0
+
+    def device_step():
+        solver.sweeps(iters)
+        core.finish_async()
+
+    for _ in range(args.warmup):
+        device_step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = core.info()["launches"]
+    times = []
+    with ClockSampler(dev) as clocks:
+        for _ in range(args.steps):
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0.record()
+            device_step()
+            e1.record()
+            torch.cuda.synchronize()
+            dist.barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
+            times.append(float(t.item()))
+    launches = torch.tensor([core.info()["launches"] - launches0], device="cuda")
+    dist.all_reduce(launches)
+    ms_per_step = float(np.mean(times))
+    value = unknowns * iters / (ms_per_step * 1e-3) / 1e9
+
+    # end to end: every rank uploads its uint8 slab from pinned memory, solves, downloads its band
+    psrc, pmask, ptgt = pinned_copy(src), pinned_copy(mask), pinned_copy(tgt)
+    e2e_t = []
+    for i in range(3):
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        solver.reset_slab(n, psrc, pmask, ptgt, work["grad"])
+        img, err = solver.step(iters)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda")
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        if i:
+            e2e_t.append(float(dt.item()))
+    e2e_s = float(np.mean(e2e_t))
+    h2d = torch.tensor([src.nbytes + mask.nbytes + tgt.nbytes], device="cuda", dtype=torch.float64)
+    d2h = torch.tensor([plan.slab_rows * m * 3 + 12], device="cuda", dtype=torch.float64)
+    dist.all_reduce(h2d)
+    dist.all_reduce(d2h)
+
+    info = core.info()
+    k = info["block_k"]
+    peak, peak_src = measured_peak()
+    # per-GPU roofline of the sweep kernel on this rank's slab (rank 0 reports)
+    band_unknowns = unknowns / world
+    achieved = GRID_BYTES_PER_UPDATE * band_unknowns * iters / (ms_per_step * 1e-3) / 1e9
+    if rank == 0:
+        line = {
+            "metric": "jacobi_gupd_per_s",
+            "value": value,
+            "unit": "Gupd/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms_per_step,
+            "higher_is_better": True,
+            "scaling": "strong",
+            "vs_baseline": None,
+            "dtype": "f32",
+            "data": "synthetic",
+            "config": {
+                "workload": f"{name}: grid solver, {n}x{m}x3 {work['mask']} mask, grad {work['grad']}, {iters} sweeps per "
+                f"step, {world} row bands, halo {halo} rows exchanged every {halo} sweeps (NCCL send/recv)",
+                "unknowns": unknowns,
+                "sweeps_per_step": iters,
+                "block_k": k,
+                "halo": halo,
+                "band_rows": plan.band_hi - plan.band_lo,
+                "l2": "per-GPU slab far exceeds the 126 MB L2; no flush needed",
+                "reset_s": reset_s,
+            },
+            "roofline": {
+                "bound": "hbm", "kernel": "grid_sweepk_pipe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": profiled_traffic("grid_sweepk_pipe_kernel"),
+                "peak_source": peak_src,
+                "note": "per-GPU effective bandwidth (36 B x unknowns of one band x sweeps / step time, halo "
+                        "exchange and epilogue included)",
+            },
+            "cpu_baseline": None,
+            "e2e": {"value": unknowns * iters / e2e_s / 1e9, "unit": "Gupd/s", "h2d_bytes_per_step": int(h2d.item()),
+                    "d2h_bytes_per_step": int(d2h.item()), "ms_per_step": e2e_s * 1e3,
+                    "api": "BandGridSolver.reset_slab(uint8 slabs) + step() per rank, pinned host buffers"},
+            "gpu_launches": int(launches.item()),
+            "clocks": clocks.summary(),
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -375,6 +517,8 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--iters", type=int, default=0, help="override sweeps per step")
     ap.add_argument("--block-k", type=int, default=0)
+    ap.add_argument("--halo", type=int, default=16, help="halo depth (rows) of the row-band sharding")
+    ap.add_argument("--size", type=int, default=0, help="override the image side")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -382,11 +526,11 @@ def main():
     work = WORKLOADS[name]
     if args.impl == "reference":
         return run_reference(args, work, name)
-    if args.gpus == 1:
+    if args.gpus == 1 and "RANK" not in os.environ:
         return run_single(args, work, name)
-    from fpie_b200 import band_bench
-
-    return band_bench.run(args, work, name)
+    if work["solver"] != "grid":
+        raise SystemExit("row-band sharding exists for the grid solver only (EquSolver: replicas, see DESIGN.md)")
+    return run_band(args, work, name)
 
 
 if __name__ == "__main__":

@@ -132,6 +132,14 @@ API int fpie_b200_grid_reset_from_images(fpie_b200_grid *g, const uint8_t *src, 
     g->impl.reset_from_images(src, sh, sw, mask, mh, mw, mc, tgt, th, tw, h0, w0, h1, w1, grad_mode, out_n, out_box4);
   });
 }
+API int fpie_b200_grid_reset_slab(fpie_b200_grid *g, const uint8_t *src, const uint8_t *mask, const uint8_t *tgt,
+                                  int rows, int cols, int mask_channels, int grad_mode) {
+  NEED(g);
+  return guarded([&] {
+    g->impl.reset_from_images(src, rows, cols, mask, rows, cols, mask_channels, tgt, rows, cols, 0, 0, 0, 0, grad_mode,
+                              nullptr, nullptr, /*crop=*/false);
+  });
+}
 API int fpie_b200_grid_band_view(fpie_b200_grid *g, int which_buffer, float **dev_base, int64_t *plane_stride,
                                  int64_t *row_pitch, int *pad_rows, int *pad_cols) {
   NEED(g);

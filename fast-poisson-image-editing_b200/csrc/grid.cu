@@ -653,11 +653,11 @@ void GridSolver::reset(int n, int m, const int32_t *mask, int64_t mask_rs, int64
 
 void GridSolver::reset_from_images(const uint8_t *src, int sh, int sw, const uint8_t *mask, int mh, int mw, int mc,
                                    const uint8_t *tgt, int th, int tw, int h0, int w0, int h1, int w1, int grad_mode,
-                                   int64_t *out_n, int32_t *out_box4) {
+                                   int64_t *out_n, int32_t *out_box4, bool crop) {
   DeviceGuard guard(device_);
   ready_ = false;
   BlendUpload up;
-  up.upload(stream_, src, sh, sw, mask, mh, mw, mc, tgt, th, tw, h0, w0, h1, w1, grad_mode);
+  up.upload(stream_, src, sh, sw, mask, mh, mw, mc, tgt, th, tw, h0, w0, h1, w1, grad_mode, crop);
   const BlendImages &b = up.images();
   layout(b.n, b.m);
   const PlaneGeom &g = geom_;

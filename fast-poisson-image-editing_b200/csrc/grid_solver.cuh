@@ -42,7 +42,7 @@ class GridSolver {
              const float *grad);
   void reset_from_images(const uint8_t *src, int sh, int sw, const uint8_t *mask, int mh, int mw, int mc,
                          const uint8_t *tgt, int th, int tw, int h0, int w0, int h1, int w1, int grad_mode,
-                         int64_t *out_n, int32_t *out_box4);
+                         int64_t *out_n, int32_t *out_box4, bool crop = true);
   void sweeps_async(int iters);
   void finish_async();
   void sync();

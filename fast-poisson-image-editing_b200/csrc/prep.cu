@@ -39,7 +39,8 @@ void BlendUpload::release() {
 }
 
 void BlendUpload::upload(cudaStream_t stream, const uint8_t *src, int sh, int sw, const uint8_t *mask, int mh, int mw,
-                         int mc, const uint8_t *tgt, int th, int tw, int h0, int w0, int h1, int w1, int mode) {
+                         int mc, const uint8_t *tgt, int th, int tw, int h0, int w0, int h1, int w1, int mode,
+                         bool crop) {
   FPIE_REQUIRE(src && mask && tgt, "reset_from_images: null image");
   FPIE_REQUIRE(sh > 0 && sw > 0 && mh > 0 && mw > 0 && th > 0 && tw > 0, "reset_from_images: empty image");
   FPIE_REQUIRE(mc == 1 || mc == 3, "reset_from_images: mask must have 1 or 3 channels");
@@ -62,6 +63,18 @@ void BlendUpload::upload(cudaStream_t stream, const uint8_t *src, int sh, int sw
   b.sh = sh; b.sw = sw; b.mh = mh; b.mw = mw; b.mc = mc; b.th = th; b.tw = tw;
   b.h0 = h0; b.w0 = w0; b.h1 = h1; b.w1 = w1;
   b.mode = mode;
+  if (!crop) {
+    // slab mode (row-band sharding): the whole mask image is the grid; its own frame acts as the
+    // fixed boundary (global frame rows, or halo rows refreshed by the neighbour band)
+    b.x0 = 0;
+    b.y0 = 0;
+    b.n = mh;
+    b.m = mw;
+    FPIE_REQUIRE(h0 >= 0 && w0 >= 0 && h0 + mh <= sh && w0 + mw <= sw, "reset: the slab falls outside the source image");
+    FPIE_REQUIRE(h1 >= 0 && w1 >= 0 && h1 + mh <= th && w1 + mw <= tw, "reset: the slab falls outside the target image");
+    img_ = b;
+    return;
+  }
   const long long total = (long long)mh * mw;
   mask_bbox_kernel<<<(int)ceil_div(total, 256), 256, 0, stream>>>(b, box_.ptr);
   CUDA_CHECK(cudaGetLastError());

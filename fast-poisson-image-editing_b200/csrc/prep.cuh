@@ -31,7 +31,7 @@ struct CropBox {
 class BlendUpload {
  public:
   void upload(cudaStream_t stream, const uint8_t *src, int sh, int sw, const uint8_t *mask, int mh, int mw, int mc,
-              const uint8_t *tgt, int th, int tw, int h0, int w0, int h1, int w1, int mode);
+              const uint8_t *tgt, int th, int tw, int h0, int w0, int h1, int w1, int mode, bool crop = true);
   const BlendImages &images() const { return img_; }
   void release();
 

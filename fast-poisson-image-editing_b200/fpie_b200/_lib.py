@@ -36,6 +36,7 @@ SIGNATURES = {
     "fpie_b200_grid_info": [c_void_p, i64p, i64p, intp, i64p, i64p],
     "fpie_b200_grid_reset_from_images": [c_void_p, u8p, c_int, c_int, u8p, c_int, c_int, c_int, u8p, c_int, c_int,
                                          c_int, c_int, c_int, c_int, c_int, i64p, i32p],
+    "fpie_b200_grid_reset_slab": [c_void_p, u8p, u8p, u8p, c_int, c_int, c_int, c_int],
     "fpie_b200_grid_band_view": [c_void_p, c_int, P(c_void_p), i64p, i64p, intp, intp],
     "fpie_b200_grid_band_current": [c_void_p, intp],
     "fpie_b200_grid_set_row_window": [c_void_p, c_int, c_int],

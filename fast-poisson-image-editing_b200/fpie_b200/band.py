@@ -1,0 +1,269 @@
+"""Row-band sharded GridSolver: one process per GPU, halo rows over NCCL.
+
+The reference's multi-worker GridSolver (fpie/core/mpi/grid.cc) cuts the grid
+into row bands with ``offset[i+1] = offset[i] + N/P + (i < N%P)`` (grid.cc:27-31)
+and swaps ONE halo row every ``S`` sweeps (grid.cc:118-135), so its bands run on
+stale neighbours in between and the result is not Jacobi.  Here every band keeps
+``halo`` rows of each neighbour, runs at most ``halo`` sweeps on its slab
+(band + halos) and then refreshes the halo rows from the neighbours' band
+edges: after ``s <= halo`` sweeps only the outer ``s`` halo rows are stale, the
+band itself is exact, so the sharded result equals single-device Jacobi bit for
+bit (modelled in ``oracle/np_oracle.grid_sweeps_banded``).
+
+``BandGridSolver`` is transport- and device-agnostic host logic: the per-rank
+compute object ("core") and the process group are injected, which is how the
+CPU test-suite runs it with ``gloo`` over a numpy stand-in core, and how the
+GPU path runs it with ``nccl`` over ``fpie_b200.GridSolver``.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+
+def band_offsets(n_rows: int, parts: int) -> list[int]:
+    """Row offsets of ``parts`` bands (fpie/core/mpi/grid.cc:27-31)."""
+    off = [0]
+    for i in range(parts):
+        off.append(off[-1] + n_rows // parts + (1 if i < n_rows % parts else 0))
+    return off
+
+
+@dataclass(frozen=True)
+class BandPlan:
+    """Geometry of one rank's slab inside the global grid (rows only)."""
+
+    rank: int
+    world: int
+    n_rows: int  # rows of the global grid
+    halo: int
+    band_lo: int  # first global row owned by this rank
+    band_hi: int  # one past the last owned row
+    slab_lo: int  # first global row held (band_lo - halo, clipped)
+    slab_hi: int
+
+    @property
+    def up(self) -> int | None:
+        """Rank owning the rows above (None at the top or for an empty band)."""
+        return self._neighbour(-1)
+
+    @property
+    def down(self) -> int | None:
+        return self._neighbour(+1)
+
+    def _neighbour(self, step: int) -> int | None:
+        if self.band_hi == self.band_lo:
+            return None
+        off = band_offsets(self.n_rows, self.world)
+        r = self.rank + step
+        while 0 <= r < self.world:
+            if off[r + 1] > off[r]:
+                return r
+            r += step
+        return None
+
+    @property
+    def local_band(self) -> tuple[int, int]:
+        """Band rows in slab-local coordinates."""
+        return self.band_lo - self.slab_lo, self.band_hi - self.slab_lo
+
+    @property
+    def slab_rows(self) -> int:
+        return self.slab_hi - self.slab_lo
+
+
+def make_plan(n_rows: int, world: int, rank: int, halo: int) -> BandPlan:
+    if halo < 1:
+        raise ValueError("halo depth must be >= 1")
+    off = band_offsets(n_rows, world)
+    lo, hi = off[rank], off[rank + 1]
+    # every non-empty band must be at least `halo` rows tall, or a neighbour's halo would
+    # reach past it into a third band
+    sizes = [off[i + 1] - off[i] for i in range(world) if off[i + 1] > off[i]]
+    if len(sizes) > 1 and min(sizes) < halo:
+        raise ValueError(f"bands of {min(sizes)} rows are shorter than the halo depth {halo}")
+    return BandPlan(rank, world, n_rows, halo, lo, hi, max(lo - halo, 0), min(hi + halo, n_rows))
+
+
+class BandGridSolver:
+    """GridSolver interface (``reset / sync / step``) over row bands.
+
+    ``core`` must provide ``reset(N, mask, tgt, grad)``, ``sweeps_async(k)``,
+    ``finish_async()``, ``fetch() -> (uint8 slab image, err[3])``,
+    ``set_row_window(lo, hi)``, ``state()`` and ``rows_view(lo, hi) -> list of
+    torch tensors`` (views of the CURRENT state rows, one contiguous tensor per
+    channel plane) -- ``fpie_b200.band.CudaBandCore`` adapts ``GridSolver``.
+    ``dist`` is ``torch.distributed`` (or any object with the same
+    ``batch_isend_irecv / P2POp / isend / irecv / all_reduce`` surface).
+    """
+
+    def __init__(self, core, dist, group=None, halo: int = 16):
+        self.core, self.dist, self.group = core, dist, group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.halo = int(halo)
+        self.plan: BandPlan | None = None
+
+    # -- reference interface -------------------------------------------------
+    def reset(self, N, mask, tgt, grad) -> None:
+        """Every rank passes the same global arrays (what ``sync()`` leaves on each
+        MPI rank in the reference, mpi/grid.cc:34-54) and keeps only its slab."""
+        mask = np.asarray(mask)
+        self.plan = make_plan(mask.shape[0], self.world, self.rank, self.halo)
+        p = self.plan
+        if p.band_hi == p.band_lo:
+            self._empty = True
+            return
+        self._empty = False
+        sl = slice(p.slab_lo, p.slab_hi)
+        self.core.reset(int(p.slab_rows * mask.shape[1]), np.ascontiguousarray(mask[sl]), tgt[sl], grad[sl])
+        self.core.set_row_window(*p.local_band)
+
+    def reset_slab(self, n_rows: int, src_slab, mask_slab, tgt_slab, gradient: str) -> BandPlan:
+        """Each rank passes only its own slab of the uint8 images (rows
+        ``plan.slab_lo:plan.slab_hi`` of the global crop, see ``make_plan``)."""
+        self.plan = make_plan(n_rows, self.world, self.rank, self.halo)
+        p = self.plan
+        self._empty = p.band_hi == p.band_lo
+        if not self._empty:
+            if src_slab.shape[0] != p.slab_rows:
+                raise ValueError(f"rank {self.rank}: slab has {src_slab.shape[0]} rows, plan needs {p.slab_rows}")
+            self.core.reset_slab(src_slab, mask_slab, tgt_slab, gradient)
+            self.core.set_row_window(*p.local_band)
+        return p
+
+    def sync(self) -> None:
+        self.dist.barrier(self.group)
+
+    def sweeps(self, iteration: int) -> None:
+        """``iteration`` Jacobi sweeps, halos refreshed every ``halo`` sweeps."""
+        left = int(iteration)
+        while left > 0:
+            s = min(self.halo, left)
+            if not self._empty:
+                self.core.sweeps_async(s)
+            self.exchange()
+            left -= s
+
+    def step(self, iteration: int):
+        """Returns ``(uint8 image of this rank's band [rows, m, 3], err[3])``; ``err``
+        is the global residual (sum over bands, as mpi/grid.cc:90-99 sums on root)."""
+        import torch
+
+        self.sweeps(iteration)
+        if self._empty:
+            img, err = np.zeros((0, 0, 3), np.uint8), np.zeros(3, np.float32)
+        else:
+            self.core.finish_async()
+            slab_img, err = self.core.fetch()
+            lo, hi = self.plan.local_band
+            img = slab_img[lo:hi]
+        total = torch.tensor(np.asarray(err, np.float64), device=self._reduce_device())
+        self.dist.all_reduce(total, group=self.group)
+        return img, total.cpu().numpy().astype(np.float32)
+
+    def band_state(self) -> np.ndarray:
+        lo, hi = self.plan.local_band
+        return self.core.state()[lo:hi]
+
+    # -- halo exchange ---------------------------------------------------------
+    def exchange(self) -> None:
+        """Send the band's edge rows to the neighbours, receive their edge rows into the halo rows."""
+        p = self.plan
+        if self._empty or (p.up is None and p.down is None):
+            return
+        dist = self.dist
+        lo, hi = p.local_band
+        ops = []
+        if p.up is not None:
+            h = lo  # halo rows actually held above the band (== self.halo away from the top edge)
+            for send, recv in zip(self.core.rows_view(lo, lo + h), self.core.rows_view(0, h)):
+                ops.append(dist.P2POp(dist.isend, send, p.up, self.group))
+                ops.append(dist.P2POp(dist.irecv, recv, p.up, self.group))
+        if p.down is not None:
+            h = p.slab_rows - hi
+            for send, recv in zip(self.core.rows_view(hi - h, hi), self.core.rows_view(hi, hi + h)):
+                ops.append(dist.P2POp(dist.isend, send, p.down, self.group))
+                ops.append(dist.P2POp(dist.irecv, recv, p.down, self.group))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+    def _reduce_device(self):
+        return getattr(self.core, "torch_device", "cpu")
+
+
+class _DeviceRows:
+    """``__cuda_array_interface__`` window onto solver-owned device memory."""
+
+    def __init__(self, ptr: int, shape: tuple[int, ...]):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class CudaBandCore:
+    """Adapts ``fpie_b200.GridSolver`` to the core protocol of ``BandGridSolver``."""
+
+    def __init__(self, solver):
+        import torch
+
+        self.solver = solver
+        self.torch_device = torch.device("cuda", solver.device)
+        self._views = {}
+
+    def reset(self, N, mask, tgt, grad):
+        self.solver.reset(N, mask, tgt, grad)
+        self._views.clear()
+
+    def reset_slab(self, src, mask, tgt, gradient):
+        self.solver.reset_slab(src, mask, tgt, gradient)
+        self._views.clear()
+
+    def sweeps_async(self, k):
+        self.solver.sweeps_async(k)
+
+    def finish_async(self):
+        self.solver.finish_async()
+
+    def fetch(self):
+        return self.solver.fetch()
+
+    def state(self):
+        return self.solver.state()
+
+    def set_row_window(self, lo, hi):
+        self.solver.set_row_window(lo, hi)
+
+    def _planes(self, which: int):
+        """torch view [3, rows_alloc_from_pad, pitch] of state buffer ``which`` (cached)."""
+        import torch
+
+        if which not in self._views:
+            v = self.solver.band_view(which)
+            n = self.solver.shape[0]
+            planes = []
+            for p in range(3):
+                ptr = v["base"] + 4 * (p * v["plane"] + v["pad_rows"] * v["pitch"])
+                planes.append(torch.as_tensor(_DeviceRows(ptr, (n, v["pitch"])), device=self.torch_device))
+            self._views[which] = planes
+        return self._views[which]
+
+    def rows_view(self, lo: int, hi: int):
+        return [plane[lo:hi] for plane in self._planes(self.solver.current_buffer())]
+
+
+def init_process_group_from_env(backend: str | None = None):
+    """``torch.distributed`` set-up for ``torchrun`` launches (RANK / WORLD_SIZE /
+    LOCAL_RANK / MASTER_ADDR / MASTER_PORT from the environment)."""
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group(backend=backend)
+    return dist

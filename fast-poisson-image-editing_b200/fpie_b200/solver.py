@@ -142,6 +142,17 @@ class GridSolver(_Handle):
         self.shape = (int(box[1] - box[0]), int(box[3] - box[2]))
         return int(out_n.value), tuple(int(v) for v in box)
 
+    def reset_slab(self, src, mask, tgt, gradient: str = "max") -> None:
+        """Load one slab of a row-band sharded problem (see ``fpie_b200.band``): three
+        uint8 images of identical size; the whole slab is the grid, its frame is fixed."""
+        s, t, mk = _as_u8_image(src, "src"), _as_u8_image(tgt, "tgt"), _as_u8_mask(mask)
+        if not (s.shape == t.shape and mk.shape[:2] == s.shape[:2]):
+            raise ValueError("slab images must have identical rows x cols")
+        _lib.check(self._lib.fpie_b200_grid_reset_slab(
+            self.handle, _ptr(s, ctypes.c_uint8), _ptr(mk, ctypes.c_uint8), _ptr(t, ctypes.c_uint8), s.shape[0],
+            s.shape[1], mk.shape[2], GRAD_CODE[gradient]))
+        self.shape = (s.shape[0], s.shape[1])
+
     def state(self) -> np.ndarray:
         n, w = self._need_shape()
         out = np.empty((n, w, 3), np.float32)

@@ -109,17 +109,29 @@ int fpie_b200_grid_reset_from_images(fpie_b200_grid *g, const uint8_t *src, int 
                                      int mh, int mw, int mc, const uint8_t *tgt, int th, int tw, int h0, int w0,
                                      int h1, int w1, int grad_mode, int64_t *out_n, int32_t *out_box4);
 
-/* Row-band sharding (multi-GPU): treat this solver as one band of a taller
- * grid.  After reset, `halo` rows above / below the band are exchanged by the
- * caller every `halo` sweeps (NCCL send/recv on the returned device
- * pointers); see fpie_b200/band.py.  rows are in grid coordinates of this
- * band's local problem.  Pointers are to float32 planes: plane p (channel)
- * row r starts at base + p*plane_stride + r*row_pitch (in floats). */
+/* ---- row-band sharding (multi-GPU GridSolver) ----------------------------
+ * One solver per GPU holds one slab = a band of rows of the global grid plus
+ * `halo` rows of its neighbours on each side (analogue of the reference's MPI
+ * row bands, fpie/core/mpi/grid.cc:21-32, 108-147, but with deep halos so the
+ * result equals single-device Jacobi bit for bit).  The caller (fpie_b200/band.py,
+ * one process per GPU) runs at most `halo` sweeps, then overwrites the halo
+ * rows of the CURRENT state buffer with the neighbour's band-edge rows
+ * (NCCL send/recv or peer copies on the device pointers below), and repeats. */
+
+/* Load one slab: src, mask, tgt are uint8 images of identical size rows x cols
+ * (mask with 1 or 3 channels), already cut to the slab's rows and to the columns
+ * of the global crop.  The whole slab is the grid (no bounding-box crop); its
+ * outer frame is fixed (global frame rows, or halo rows the exchange refreshes). */
+int fpie_b200_grid_reset_slab(fpie_b200_grid *g, const uint8_t *src, const uint8_t *mask, const uint8_t *tgt, int rows,
+                              int cols, int mask_channels, int grad_mode);
+/* Device view of state buffer `which_buffer` (0/1): grid pixel (r, c) of channel
+ * p is the float at dev_base[p * plane_stride + (r + pad_rows) * row_pitch + c + pad_cols]. */
 int fpie_b200_grid_band_view(fpie_b200_grid *g, int which_buffer, float **dev_base, int64_t *plane_stride,
                              int64_t *row_pitch, int *pad_rows, int *pad_cols);
+/* Which of the two buffers holds the current state (it flips every pass). */
 int fpie_b200_grid_band_current(fpie_b200_grid *g, int *which_buffer);
-/* Restrict the sweeps of the next fpie_b200_grid_sweeps_async calls to grid
- * rows [row_lo, row_hi) (the shrinking trapezoid between halo exchanges). */
+/* Restrict the residual of the following step / finish calls to grid rows
+ * [row_lo, row_hi) -- a band counts only its own rows, not its halo. */
 int fpie_b200_grid_set_row_window(fpie_b200_grid *g, int row_lo, int row_hi);
 
 /* ---- EquSolver ----------------------------------------------------------

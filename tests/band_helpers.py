@@ -1,0 +1,110 @@
+"""Shared pieces of the row-band tests: a numpy stand-in core (backed by the
+oracle -- test infrastructure) and an in-process thread transport."""
+
+import queue
+import threading
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from oracle import np_oracle
+
+
+class OracleBandCore:
+    """Core protocol of ``fpie_b200.band.BandGridSolver`` on the CPU: the slab is
+    swept by the numpy oracle with its outer frame held fixed, exactly what the
+    CUDA GridSolver does to a slab."""
+
+    torch_device = "cpu"
+
+    def reset(self, N, mask, tgt, grad):
+        m = np.array(mask, np.int32, copy=True)
+        m[0, :] = m[-1, :] = 0
+        m[:, 0] = m[:, -1] = 0  # GridSolver treats the grid frame as unmasked
+        self.mask = m
+        self.grad = np.array(grad, np.float32, copy=True)
+        self.planes = np.ascontiguousarray(np.asarray(tgt, np.float32).transpose(2, 0, 1))
+        self.window = (0, m.shape[0])
+
+    def _aos(self):
+        return self.planes.transpose(1, 2, 0)
+
+    def sweeps_async(self, k):
+        out = np_oracle.grid_sweeps(self.mask, self._aos(), self.grad, k)
+        self.planes[...] = out.transpose(2, 0, 1)
+
+    def set_row_window(self, lo, hi):
+        self.window = (lo, hi)
+
+    def finish_async(self):
+        pass
+
+    def fetch(self):
+        lo, hi = self.window
+        t = np.ascontiguousarray(self._aos())
+        m = self.mask.copy()
+        m[:lo] = 0
+        m[hi:] = 0
+        return np_oracle.clip_u8(t), np_oracle.grid_residual_f64(m, t, self.grad)
+
+    def state(self):
+        return np.ascontiguousarray(self._aos())
+
+    def rows_view(self, lo, hi):
+        return [torch.from_numpy(self.planes[p, lo:hi]) for p in range(3)]
+
+
+class ThreadDist:
+    """Minimal ``torch.distributed`` look-alike for ranks living in threads of one
+    process (lets a single GPU exercise the CUDA halo path)."""
+
+    P2POp = namedtuple("P2POp", "op tensor peer group")
+    isend, irecv = "isend", "irecv"
+
+    def __init__(self, world):
+        self.world = world
+        self.local = threading.local()
+        self.q = {(a, b): queue.Queue() for a in range(world) for b in range(world)}
+        self.bar = threading.Barrier(world)
+        self.slots = [None] * world
+
+    def bind(self, rank):
+        self.local.rank = rank
+
+    def get_rank(self, group=None):
+        return self.local.rank
+
+    def get_world_size(self, group=None):
+        return self.world
+
+    def barrier(self, group=None):
+        self.bar.wait()
+
+    def batch_isend_irecv(self, ops):
+        me = self.local.rank
+        for op in ops:
+            if op.op == "isend":
+                self.q[(me, op.peer)].put(op.tensor.clone())
+        for op in ops:
+            if op.op == "irecv":
+                op.tensor.copy_(self.q[(op.peer, me)].get(timeout=120))
+        return []
+
+    def all_reduce(self, tensor, group=None):
+        me = self.local.rank
+        self.slots[me] = tensor.clone()
+        self.bar.wait()
+        total = sum(s.to(tensor.device) for s in self.slots)
+        self.bar.wait()
+        tensor.copy_(total)
+
+
+def random_grid(n, m, seed, density=0.7):
+    rng = np.random.default_rng(seed)
+    mask = np.zeros((n, m), np.int32)
+    mask[1:-1, 1:-1] = rng.random((n - 2, m - 2)) < density
+    tgt = rng.integers(0, 256, (n, m, 3)).astype(np.float32)
+    grad = (rng.integers(-2040, 2041, (n, m, 3)) / 2).astype(np.float32)
+    grad[mask == 0] = 0
+    return mask, tgt, grad

@@ -1,0 +1,146 @@
+"""Row-band sharded GridSolver on the GPU.
+
+* one GPU: the bands live in threads of this process (ThreadDist), each with
+  its own ``fpie_b200.GridSolver`` slab; halo rows move as device copies through
+  the same ``rows_view`` tensors NCCL would use;
+* >= 2 GPUs: real ``torch.distributed`` NCCL ranks, one process per GPU.
+
+In both cases the stitched fp32 state must equal single-solver Jacobi bit for
+bit, and the all-reduced err must equal the global residual."""
+
+import os
+import socket
+import sys
+import threading
+
+import numpy as np
+import pytest
+from band_helpers import ThreadDist, random_grid
+from conftest import PKG_ROOT, ROOT
+
+from oracle import c_oracle, np_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_threads(world, halo, make_and_reset, steps):
+    import torch
+
+    import fpie_b200
+    from fpie_b200 import band
+
+    dist = ThreadDist(world)
+    out = [None] * world
+    errors = []
+
+    def work(rank):
+        try:
+            dist.bind(rank)
+            torch.cuda.set_device(0)
+            solver = band.BandGridSolver(band.CudaBandCore(fpie_b200.GridSolver(8, 8, device=0)), dist, halo=halo)
+            make_and_reset(solver)
+            solver.sync()
+            for it in steps:
+                img, err = solver.step(it)
+            out[rank] = (solver.plan, solver.band_state(), img, err)
+        except Exception as exc:  # surface in the main thread
+            errors.append(exc)
+            try:
+                dist.bar.abort()
+            except Exception:
+                pass
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return out
+
+
+@pytest.mark.parametrize("world,halo,steps", [(2, 8, (37,)), (3, 16, (5, 40)), (4, 24, (64,))])
+def test_thread_bands_core_level(world, halo, steps):
+    shape = (530, 301)
+    mask, tgt, grad = random_grid(*shape, seed=8)
+    out = _run_threads(world, halo, lambda s: s.reset(mask.size, mask, tgt, grad), steps)
+    want = c_oracle.grid_sweeps(mask, tgt, grad, sum(steps))
+    got = np.zeros_like(want)
+    for plan, state, img, err in out:
+        got[plan.band_lo : plan.band_hi] = state
+        np.testing.assert_array_equal(img, c_oracle.clip_u8(want[plan.band_lo : plan.band_hi]))
+        np.testing.assert_allclose(err, c_oracle.grid_residual(mask, want, grad)[1], rtol=1e-5)
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("kind", ["square", "circle"])
+def test_thread_bands_from_image_slabs(kind):
+    """Each band uploads only its slab of the uint8 images (reset_slab)."""
+    from fpie_b200 import band, synth
+
+    n, m, world, halo, iters = 700, 640, 3, 16, 48
+    src, mask, tgt = synth.make_problem(kind, n, m, seed=3)
+    # global canonical crop (host side, cheap): the slabs are cut from it
+    mc, tcrop, g, box = np_oracle.grid_system(src, mask, tgt, (0, 0), (0, 0), "max")
+    x0, x1, y0, y1 = box
+    csrc, cmask, ctgt = src[x0:x1, y0:y1], (mc * 255).astype(np.uint8), tgt[x0:x1, y0:y1]
+
+    def reset(solver):
+        p = band.make_plan(x1 - x0, solver.world, solver.rank, halo)
+        sl = slice(p.slab_lo, p.slab_hi)
+        solver.reset_slab(x1 - x0, csrc[sl], cmask[sl], ctgt[sl], "max")
+
+    out = _run_threads(world, halo, reset, (iters,))
+    want = c_oracle.grid_sweeps(mc, tcrop, g, iters)
+    for plan, state, img, err in out:
+        np.testing.assert_array_equal(state, want[plan.band_lo : plan.band_hi])
+        np.testing.assert_allclose(err, c_oracle.grid_residual(mc, want, g)[1], rtol=1e-5)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _nccl_worker(rank, world, port, out_dir):
+    for p in (ROOT, PKG_ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+
+    import fpie_b200
+    from fpie_b200 import band
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    try:
+        mask, tgt, grad = random_grid(900, 517, seed=2)
+        solver = band.BandGridSolver(band.CudaBandCore(fpie_b200.GridSolver(8, 8, device=rank)), dist, halo=16)
+        solver.reset(mask.size, mask, tgt, grad)
+        solver.sync()
+        solver.step(20)
+        img, err = solver.step(45)
+        p = solver.plan
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), state=solver.band_state(), err=err, lo=p.band_lo, hi=p.band_hi)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nccl_bands(tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    mp.spawn(_nccl_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mask, tgt, grad = random_grid(900, 517, seed=2)
+    want = c_oracle.grid_sweeps(mask, tgt, grad, 65)
+    for r in range(world):
+        z = np.load(tmp_path / f"rank{r}.npz")
+        np.testing.assert_array_equal(z["state"], want[int(z["lo"]) : int(z["hi"])])
+        np.testing.assert_allclose(z["err"], c_oracle.grid_residual(mask, want, grad)[1], rtol=1e-5)
