@@ -10,6 +10,7 @@ Jacobi sweeps + residual + uint8 conversion.  Workloads (BASELINE.json configs):
     cfg3  EquSolver,  8192x8192x3 ring mask,   grad avg, 10000 sweeps
     cfg4  GridSolver, 32768x32768x3 square mask, row bands over N GPUs, 5000 sweeps (N>1 default)
     cfg1  EquSolver,  1026x1026x3 square mask, grad max, 5000 sweeps
+    cfg5  GridSolver, 512 independent 256x256x3 patches (one mosaic), grad src, 5000 sweeps
 
 Prints ONE JSON line (rank 0).  ``value`` is timed with CUDA events with the
 inputs resident in HBM; ``e2e`` goes through the Processor API with host
@@ -44,6 +45,7 @@ WORKLOADS = {
     "cfg2": dict(solver="grid", size=4096, mask="circle", grad="max", iters=5000),
     "cfg3": dict(solver="equ", size=8192, mask="ring", grad="avg", iters=10000),
     "cfg4": dict(solver="grid", size=32768, mask="square", grad="max", iters=5000),
+    "cfg5": dict(solver="batch", size=256, batch=512, mask="square", grad="src", iters=5000),
 }
 
 
@@ -246,13 +248,25 @@ def run_single(args, work, name):
     dev = 0
     torch.cuda.set_device(dev)
     size, iters = (args.size or work["size"]), (args.iters or work["iters"])
-    src, mask, tgt = synth.make_problem(work["mask"], size, size, seed=0)
-    is_grid = work["solver"] == "grid"
-    Proc = fpie_b200.GridProcessor if is_grid else fpie_b200.EquProcessor
-    kw = dict(block_k=args.block_k) if is_grid else {}
-    proc = Proc(work["grad"], "b200", device=dev, **kw)
+    is_batch = work["solver"] == "batch"
+    is_grid = work["solver"] in ("grid", "batch")
+    if is_batch:
+        rng = np.random.default_rng(0)
+        nb = work["batch"]
+        src = rng.integers(0, 256, (nb, size, size, 3), dtype=np.uint8)
+        tgt = rng.integers(0, 256, (nb, size, size, 3), dtype=np.uint8)
+        mask = np.full((nb, size, size), 255, np.uint8)
+        proc = fpie_b200.BatchGridProcessor(work["grad"], "b200", device=dev, block_k=args.block_k)
+        reset_args = (src, mask, tgt)
+    else:
+        src, mask, tgt = synth.make_problem(work["mask"], size, size, seed=0)
+        Proc = fpie_b200.GridProcessor if is_grid else fpie_b200.EquProcessor
+        kw = dict(block_k=args.block_k) if is_grid else {}
+        proc = Proc(work["grad"], "b200", device=dev, **kw)
+        reset_args = (src, mask, tgt, (0, 0), (0, 0))
+    Proc = type(proc)
     t0 = time.perf_counter()
-    nvars = proc.reset(src, mask, tgt, (0, 0), (0, 0))
+    nvars = proc.reset(*reset_args)
     reset_s = time.perf_counter() - t0
     core = proc.core
     info0 = core.info()
@@ -291,7 +305,7 @@ def run_single(args, work, name):
     sweeps_per_launch = iters / sweep_launches
     achieved = per_update * unknowns * sweeps_per_launch / launch_s / 1e9
     peak, peak_src = measured_peak()
-    kernel = "grid_sweepk_kernel" if is_grid else "equ_sweep_kernel"
+    kernel = "grid_sweepk_pipe_kernel" if is_grid else "equ_sweep_kernel"
     roofline = {
         "bound": "hbm",
         "kernel": kernel,
@@ -312,13 +326,13 @@ def run_single(args, work, name):
     for i in range(max(2, min(args.steps, 3)) + 1):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        proc.reset(psrc, pmask, ptgt, (0, 0), (0, 0))
+        proc.reset(psrc, pmask, ptgt, *reset_args[3:])
         out, err = proc.step(iters)
         torch.cuda.synchronize()
         if i:
             e2e_s.append(time.perf_counter() - t0)
     e2e_val = unknowns * iters / float(np.mean(e2e_s)) / 1e9
-    crop_bytes = int(np.prod(core.shape if is_grid else core.crop_shape)) * 3
+    crop_bytes = int(np.prod(core.batch_shape if is_batch else core.shape if is_grid else core.crop_shape)) * 3
     e2e = {
         "value": e2e_val,
         "unit": "Gupd/s",
@@ -330,7 +344,12 @@ def run_single(args, work, name):
 
     base = None
     if not args.no_cpu_baseline:
-        base, _, _, _ = cpu_baseline(work, src, mask, tgt, budget_s=args.cpu_budget)
+        if is_batch:  # one patch after the other on the host, as the reference GUI does; sample = first patches
+            w1 = dict(work, solver="grid")
+            base, _, _, _ = cpu_baseline(w1, src[0], mask[0], tgt[0], budget_s=args.cpu_budget)
+            base["sample"] = "patch 0 of the batch: " + base["sample"]
+        else:
+            base, _, _, _ = cpu_baseline(work, src, mask, tgt, budget_s=args.cpu_budget)
 
     line = {
         "metric": "jacobi_gupd_per_s",
@@ -346,8 +365,8 @@ def run_single(args, work, name):
         "dtype": "f32",
         "data": "synthetic",
         "config": {
-            "workload": f"{name}: {work['solver']} solver, {size}x{size}x3 {work['mask']} mask, grad {work['grad']}, "
-            f"{iters} sweeps per step",
+            "workload": f"{name}: {work['solver']} solver, {(str(work['batch']) + ' patches of ') if is_batch else ''}"
+            f"{size}x{size}x3 {work['mask']} mask, grad {work['grad']}, {iters} sweeps per step",
             "unknowns": unknowns,
             "n_vars": nvars,
             "sweeps_per_step": iters,

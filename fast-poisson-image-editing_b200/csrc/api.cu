@@ -92,6 +92,10 @@ API int fpie_b200_grid_step(fpie_b200_grid *g, int iters, uint8_t *out_img, floa
   NEED(g);
   return guarded([&] { g->impl.step(iters, out_img, out_err3); });
 }
+API int fpie_b200_grid_step_into(fpie_b200_grid *g, int iters, uint8_t *dst, int64_t dst_row_stride, float *out_err3) {
+  NEED(g);
+  return guarded([&] { g->impl.step(iters, dst, out_err3, dst_row_stride); });
+}
 API int fpie_b200_grid_state(fpie_b200_grid *g, float *out_state) {
   NEED(g);
   return guarded([&] { g->impl.state(out_state); });
@@ -131,6 +135,11 @@ API int fpie_b200_grid_reset_from_images(fpie_b200_grid *g, const uint8_t *src, 
   return guarded([&] {
     g->impl.reset_from_images(src, sh, sw, mask, mh, mw, mc, tgt, th, tw, h0, w0, h1, w1, grad_mode, out_n, out_box4);
   });
+}
+API int fpie_b200_grid_reset_batch(fpie_b200_grid *g, const uint8_t *src, const uint8_t *mask, const uint8_t *tgt,
+                                   int batch, int rows, int cols, int mask_channels, int grad_mode) {
+  NEED(g);
+  return guarded([&] { g->impl.reset_batch(src, mask, tgt, batch, rows, cols, mask_channels, grad_mode); });
 }
 API int fpie_b200_grid_reset_slab(fpie_b200_grid *g, const uint8_t *src, const uint8_t *mask, const uint8_t *tgt,
                                   int rows, int cols, int mask_channels, int grad_mode) {

@@ -462,7 +462,7 @@ __device__ __forceinline__ float resid_term(float t, float hq, float up, float d
 
 // grid: (blocks over rows x groups, plane).  err[plane % 3] accumulates in double.
 __global__ void __launch_bounds__(256)
-grid_residual_kernel(PlaneGeom g, int row_lo, int row_hi, const uint32_t *__restrict__ bits,
+grid_residual_kernel(PlaneGeom g, BatchMap bm, int row_lo, int row_hi, const uint32_t *__restrict__ bits,
                      const float *__restrict__ x, const float *__restrict__ hq, double *__restrict__ err) {
   const int p = blockIdx.y;
   const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -481,6 +481,15 @@ grid_residual_kernel(PlaneGeom g, int row_lo, int row_hi, const uint32_t *__rest
       if (nib & 4u) acc += resid_term(c.z, h.z, u.z, d.z, c.y, c.w);
       if (nib & 8u) acc += resid_term(c.w, h.w, u.w, d.w, c.z, rt);
     }
+  }
+  if (bm.batch > 0) {
+    // one residual triple per patch: groups never straddle patches (pw % 4 == 0), lanes of a warp may
+    if (acc != 0.f) {
+      const int r = row_lo + (int)(q / g.groups), grp = (int)(q % g.groups);
+      const int id = (r / bm.ph) * bm.bcols + (4 * grp) / bm.pw;
+      atomicAdd(&err[(long long)id * 3 + p], (double)acc);
+    }
+    return;
   }
   // warp shuffle reduction, then one partial per warp through shared memory
   double v = (double)acc;
@@ -502,7 +511,7 @@ __device__ __forceinline__ uint32_t clip_u8(float v) { return __float2uint_rz(fm
 
 // thread = 4 pixels x 3 channels -> 12 interleaved bytes of img[n, m, 3]
 __global__ void __launch_bounds__(256)
-grid_to_u8_kernel(PlaneGeom g, const float *__restrict__ x, uint8_t *__restrict__ img) {
+grid_to_u8_kernel(PlaneGeom g, BatchMap bm, const float *__restrict__ x, uint8_t *__restrict__ img) {
   const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (q >= (long long)g.n * g.groups) return;
   const int r = (int)(q / g.groups), grp = (int)(q % g.groups);
@@ -511,7 +520,13 @@ grid_to_u8_kernel(PlaneGeom g, const float *__restrict__ x, uint8_t *__restrict_
   const uint32_t a0 = clip_u8(a.x), a1 = clip_u8(a.y), a2 = clip_u8(a.z), a3 = clip_u8(a.w);
   const uint32_t b0 = clip_u8(b.x), b1 = clip_u8(b.y), b2 = clip_u8(b.z), b3 = clip_u8(b.w);
   const uint32_t c0 = clip_u8(c.x), c1 = clip_u8(c.y), c2 = clip_u8(c.z), c3 = clip_u8(c.w);
-  const long long o = ((long long)r * g.m + 4 * grp) * 3;
+  long long o = ((long long)r * g.m + 4 * grp) * 3;
+  if (bm.batch > 0) {  // mosaic -> [batch, ph, pw, 3]
+    const int by = r / bm.ph, bx = (4 * grp) / bm.pw;
+    const int id = by * bm.bcols + bx;
+    if (id >= bm.batch) return;
+    o = (((long long)id * bm.ph + (r - by * bm.ph)) * bm.pw + (4 * grp - bx * bm.pw)) * 3;
+  }
   const int valid = min(4, g.m - 4 * grp);
   if (valid == 4 && (o & 3) == 0) {
     uint32_t *dst = reinterpret_cast<uint32_t *>(img + o);
@@ -537,8 +552,10 @@ grid_build_kernel(PlaneGeom g, BlendImages b, uint32_t *__restrict__ bits, float
   const int r = (int)(warp / g.wpitch);
   const int pcol = (int)(warp % g.wpitch) * 32 + lane;
   const int c = pcol - g.padc;
-  const bool inside = c >= 0 && c < g.m;
-  const bool on = inside && canonical_mask_at(b, b.x0 + r, b.y0 + c);
+  BlendImages pb;
+  int pr = r, pc2 = c;
+  const bool inside = c >= 0 && c < g.m && patch_view(b, r, c, pb, pr, pc2);
+  const bool on = inside && canonical_mask_at(pb, pb.x0 + pr, pb.y0 + pc2);
   const uint32_t word = __ballot_sync(0xffffffffu, on);
   const long long prow = r + g.padr;
   if (lane == 0) {
@@ -549,10 +566,10 @@ grid_build_kernel(PlaneGeom g, BlendImages b, uint32_t *__restrict__ bits, float
   const long long off = prow * g.pitch + pcol;
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
-    const float t = target_at(b, r, c, ch);
+    const float t = target_at(pb, pr, pc2, ch);
     x0[ch * g.plane + off] = t;
     x1[ch * g.plane + off] = t;
-    hq[ch * g.plane + off] = on ? 0.25f * pixel_gradient(b, r, c, ch) : 0.f;
+    hq[ch * g.plane + off] = on ? 0.25f * pixel_gradient(pb, pr, pc2, ch) : 0.f;
   }
 }
 
@@ -618,6 +635,7 @@ void GridSolver::reset(int n, int m, const int32_t *mask, int64_t mask_rs, int64
   FPIE_REQUIRE(mask_cs == 1 && mask_rs >= m, "GridSolver.reset: mask rows must be contiguous (column stride 1)");
   DeviceGuard guard(device_);
   ready_ = false;
+  batch_ = BatchMap{0, 0, 0, 0};
   layout(n, m);
   const PlaneGeom &g = geom_;
   const size_t pixels = (size_t)n * m;
@@ -656,9 +674,39 @@ void GridSolver::reset_from_images(const uint8_t *src, int sh, int sw, const uin
                                    int64_t *out_n, int32_t *out_box4, bool crop) {
   DeviceGuard guard(device_);
   ready_ = false;
-  BlendUpload up;
+  BlendUpload &up = upload_;  // device copies of the images are kept between resets (no malloc / free per call)
   up.upload(stream_, src, sh, sw, mask, mh, mw, mc, tgt, th, tw, h0, w0, h1, w1, grad_mode, crop);
+  batch_ = BatchMap{0, 0, 0, 0};
+  build_from_upload();
   const BlendImages &b = up.images();
+  if (out_n) *out_n = (int64_t)geom_.n * geom_.m;
+  if (out_box4) {
+    out_box4[0] = b.h1 + b.x0;
+    out_box4[1] = b.h1 + b.x0 + b.n;
+    out_box4[2] = b.w1 + b.y0;
+    out_box4[3] = b.w1 + b.y0 + b.m;
+  }
+}
+
+// `batch` independent patches of ph x pw pixels, solved together as one mosaic grid
+// (bcols patches per mosaic row).  Every patch keeps its own unmasked frame, so
+// the patches do not interact; the mosaic just feeds the tiled kernel full-width rows.
+void GridSolver::reset_batch(const uint8_t *src, const uint8_t *mask, const uint8_t *tgt, int batch, int ph, int pw,
+                             int mc, int grad_mode) {
+  DeviceGuard guard(device_);
+  ready_ = false;
+  FPIE_REQUIRE(pw % 4 == 0, "reset_batch: patch width must be a multiple of 4");
+  // aim for a roughly square mosaic that is at least 4096 pixels wide when the batch allows it
+  int bcols = 1;
+  while (bcols * pw < 4096 && bcols < batch) bcols *= 2;
+  upload_.upload_batch(stream_, src, mask, tgt, batch, ph, pw, mc, grad_mode, bcols);
+  batch_ = BatchMap{batch, ph, pw, bcols};
+  batch_err_.resize((size_t)batch * 3);
+  build_from_upload();
+}
+
+void GridSolver::build_from_upload() {
+  const BlendImages &b = upload_.images();
   layout(b.n, b.m);
   const PlaneGeom &g = geom_;
   for (auto &buf : x_) buf.resize((size_t)g.plane * 3);
@@ -676,13 +724,6 @@ void GridSolver::reset_from_images(const uint8_t *src, int sh, int sw, const uin
   CUDA_CHECK(cudaGetLastError());
   stats_.launches += 2;
   after_state_loaded();
-  if (out_n) *out_n = (int64_t)g.n * g.m;
-  if (out_box4) {
-    out_box4[0] = b.h1 + b.x0;
-    out_box4[1] = b.h1 + b.x0 + b.n;
-    out_box4[2] = b.w1 + b.y0;
-    out_box4[3] = b.w1 + b.y0 + b.m;
-  }
 }
 
 void GridSolver::after_state_loaded() {
@@ -906,14 +947,16 @@ void GridSolver::finish_async() {
   DeviceGuard guard(device_);
   const PlaneGeom &g = geom_;
   CUDA_CHECK(cudaMemsetAsync(err_.ptr, 0, 3 * sizeof(double), stream_));
+  if (batch_.batch > 0) CUDA_CHECK(cudaMemsetAsync(batch_err_.ptr, 0, batch_err_.bytes(), stream_));
   const long long work = (long long)(win_hi_ - win_lo_) * g.groups;
   if (work > 0 && stats_.unknowns > 0) {
     dim3 grid(blocks_for(work, 256), 3);
-    grid_residual_kernel<<<grid, 256, 0, stream_>>>(g, win_lo_, win_hi_, bits_.ptr, x_[cur_].ptr, hq_.ptr, err_.ptr);
+    grid_residual_kernel<<<grid, 256, 0, stream_>>>(g, batch_, win_lo_, win_hi_, bits_.ptr, x_[cur_].ptr, hq_.ptr,
+                                                    batch_.batch > 0 ? batch_err_.ptr : err_.ptr);
     CUDA_CHECK(cudaGetLastError());
     stats_.launches += 1;
   }
-  grid_to_u8_kernel<<<blocks_for((long long)g.n * g.groups, 256), 256, 0, stream_>>>(g, x_[cur_].ptr, img_.ptr);
+  grid_to_u8_kernel<<<blocks_for((long long)g.n * g.groups, 256), 256, 0, stream_>>>(g, batch_, x_[cur_].ptr, img_.ptr);
   CUDA_CHECK(cudaGetLastError());
   stats_.launches += 1;
   CUDA_CHECK(cudaMemcpyAsync(host_err_, err_.ptr, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
@@ -924,20 +967,34 @@ void GridSolver::sync() {
   CUDA_CHECK(cudaStreamSynchronize(stream_));
 }
 
-void GridSolver::fetch(uint8_t *out_img, float *out_err3) {
+void GridSolver::fetch(uint8_t *out_img, float *out_err3, int64_t row_stride) {
   require_ready();
   DeviceGuard guard(device_);
-  if (out_img)
-    CUDA_CHECK(cudaMemcpyAsync(out_img, img_.ptr, (size_t)geom_.n * geom_.m * 3, cudaMemcpyDeviceToHost, stream_));
+  const size_t row_bytes = (size_t)geom_.m * 3;
+  if (row_stride <= 0) row_stride = (int64_t)row_bytes;
+  FPIE_REQUIRE((size_t)row_stride >= row_bytes, "fetch: destination row stride is smaller than a row");
+  if (out_img && batch_.batch > 0)  // [batch, ph, pw, 3], packed
+    CUDA_CHECK(cudaMemcpyAsync(out_img, img_.ptr, (size_t)batch_.batch * batch_.ph * batch_.pw * 3,
+                               cudaMemcpyDeviceToHost, stream_));
+  else if (out_img)
+    CUDA_CHECK(cudaMemcpy2DAsync(out_img, (size_t)row_stride, img_.ptr, row_bytes, row_bytes, geom_.n,
+                                 cudaMemcpyDeviceToHost, stream_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));
-  if (out_err3)
-    for (int c = 0; c < 3; ++c) out_err3[c] = (float)host_err_[c];
+  if (out_err3) {
+    if (batch_.batch > 0) {  // [batch, 3]
+      std::vector<double> e((size_t)batch_.batch * 3);
+      CUDA_CHECK(cudaMemcpy(e.data(), batch_err_.ptr, e.size() * sizeof(double), cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < e.size(); ++i) out_err3[i] = (float)e[i];
+    } else {
+      for (int c = 0; c < 3; ++c) out_err3[c] = (float)host_err_[c];
+    }
+  }
 }
 
-void GridSolver::step(int iters, uint8_t *out_img, float *out_err3) {
+void GridSolver::step(int iters, uint8_t *out_img, float *out_err3, int64_t row_stride) {
   sweeps_async(iters);
   finish_async();
-  fetch(out_img, out_err3);
+  fetch(out_img, out_err3, row_stride);
 }
 
 void GridSolver::state(float *out) {

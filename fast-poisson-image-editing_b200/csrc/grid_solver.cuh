@@ -8,6 +8,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "prep.cuh"
 
 namespace fpie {
 
@@ -43,11 +44,13 @@ class GridSolver {
   void reset_from_images(const uint8_t *src, int sh, int sw, const uint8_t *mask, int mh, int mw, int mc,
                          const uint8_t *tgt, int th, int tw, int h0, int w0, int h1, int w1, int grad_mode,
                          int64_t *out_n, int32_t *out_box4, bool crop = true);
+  void reset_batch(const uint8_t *src, const uint8_t *mask, const uint8_t *tgt, int batch, int ph, int pw, int mc,
+                   int grad_mode);
   void sweeps_async(int iters);
   void finish_async();
   void sync();
-  void fetch(uint8_t *out_img, float *out_err3);
-  void step(int iters, uint8_t *out_img, float *out_err3);
+  void fetch(uint8_t *out_img, float *out_err3, int64_t row_stride = 0);
+  void step(int iters, uint8_t *out_img, float *out_err3, int64_t row_stride = 0);
   void state(float *out);
   void set_row_window(int lo, int hi);
   void band_view(int which, float **base, int64_t *plane_stride, int64_t *row_pitch, int *pad_rows, int *pad_cols);
@@ -64,6 +67,7 @@ class GridSolver {
   void build_tiles();
   void after_state_loaded();
   void make_tensor_maps();
+  void build_from_upload();
   static TileShape shape_for(int variant);
 
   int device_;
@@ -86,6 +90,9 @@ class GridSolver {
   bool force_h32_ = false;
   DeviceBuffer<uint32_t> bits_;
   DeviceBuffer<float> stage_;
+  BlendUpload upload_;
+  BatchMap batch_{0, 0, 0, 0};
+  DeviceBuffer<double> batch_err_;
   DeviceBuffer<int32_t> mask_stage_;
   DeviceBuffer<uint8_t> img_;
   DeviceBuffer<double> err_;  // [3] residual sums + [1] unknown count (as double)

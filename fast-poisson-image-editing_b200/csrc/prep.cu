@@ -38,6 +38,35 @@ void BlendUpload::release() {
   tgt_.release();
 }
 
+void BlendUpload::upload_batch(cudaStream_t stream, const uint8_t *src, const uint8_t *mask, const uint8_t *tgt,
+                               int batch, int ph, int pw, int mc, int mode, int bcols) {
+  FPIE_REQUIRE(src && mask && tgt, "reset_batch: null image");
+  FPIE_REQUIRE(batch > 0 && ph > 0 && pw > 0 && bcols > 0, "reset_batch: empty batch");
+  FPIE_REQUIRE(mc == 1 || mc == 3, "reset_batch: mask must have 1 or 3 channels");
+  FPIE_REQUIRE(mode >= 0 && mode <= 2, "reset_batch: unknown gradient mode");
+  const size_t px = (size_t)batch * ph * pw;
+  src_.resize(px * 3);
+  mask_.resize(px * mc);
+  tgt_.resize(px * 3);
+  CUDA_CHECK(cudaMemcpyAsync(src_.ptr, src, px * 3, cudaMemcpyHostToDevice, stream));
+  CUDA_CHECK(cudaMemcpyAsync(mask_.ptr, mask, px * mc, cudaMemcpyHostToDevice, stream));
+  CUDA_CHECK(cudaMemcpyAsync(tgt_.ptr, tgt, px * 3, cudaMemcpyHostToDevice, stream));
+  BlendImages b{};
+  b.src = src_.ptr;
+  b.mask = mask_.ptr;
+  b.tgt = tgt_.ptr;
+  b.sh = b.mh = b.th = ph;
+  b.sw = b.mw = b.tw = pw;
+  b.mc = mc;
+  b.mode = mode;
+  b.batch = batch;
+  b.bcols = bcols;
+  const int brows = (int)ceil_div(batch, bcols);
+  b.n = brows * ph;
+  b.m = bcols * pw;
+  img_ = b;
+}
+
 void BlendUpload::upload(cudaStream_t stream, const uint8_t *src, int sh, int sw, const uint8_t *mask, int mh, int mw,
                          int mc, const uint8_t *tgt, int th, int tw, int h0, int w0, int h1, int w1, int mode,
                          bool crop) {

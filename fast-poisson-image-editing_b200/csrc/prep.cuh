@@ -19,6 +19,14 @@ struct BlendImages {
   int x0, y0, n, m;
   int h0, w0, h1, w1;
   int mode;  // FPIE_B200_GRAD_*
+  // batch mode (batch > 0): src / mask / tgt hold `batch` patches of mh x mw pixels back to back;
+  // the grid is a mosaic of bcols patches per row, each patch keeping its own fixed frame
+  int batch, bcols;
+};
+
+// Batch mosaic geometry shared by the output kernels (batch == 0: plain image).
+struct BatchMap {
+  int batch, ph, pw, bcols;
 };
 
 struct CropBox {
@@ -32,6 +40,9 @@ class BlendUpload {
  public:
   void upload(cudaStream_t stream, const uint8_t *src, int sh, int sw, const uint8_t *mask, int mh, int mw, int mc,
               const uint8_t *tgt, int th, int tw, int h0, int w0, int h1, int w1, int mode, bool crop = true);
+  // `batch` patches of ph x pw pixels each (src / tgt [batch, ph, pw, 3], mask [batch, ph, pw, mc])
+  void upload_batch(cudaStream_t stream, const uint8_t *src, const uint8_t *mask, const uint8_t *tgt, int batch, int ph,
+                    int pw, int mc, int mode, int bcols);
   const BlendImages &images() const { return img_; }
   void release();
 
@@ -49,6 +60,25 @@ __device__ __forceinline__ bool canonical_mask_at(const BlendImages &b, int r, i
   const uint8_t *p = b.mask + ((long long)r * b.mw + c) * b.mc;
   const int s = (b.mc == 3) ? (int)p[0] + (int)p[1] + (int)p[2] : (int)p[0];
   return s >= 128 * b.mc;
+}
+
+// In batch mode, re-base the image pointers on the patch that holds mosaic pixel
+// (i, j) and return the patch-local coordinates; false if (i, j) is in no patch.
+__device__ __forceinline__ bool patch_view(const BlendImages &b, int i, int j, BlendImages &pb, int &pi, int &pj) {
+  pb = b;
+  pi = i;
+  pj = j;
+  if (b.batch <= 0) return true;
+  const int by = i / b.mh, bx = j / b.mw;
+  const int id = by * b.bcols + bx;
+  if (bx >= b.bcols || id >= b.batch) return false;
+  const long long base = (long long)id * b.mh * b.mw;
+  pb.src += base * 3;
+  pb.tgt += base * 3;
+  pb.mask += base * b.mc;
+  pi = i - by * b.mh;
+  pj = j - bx * b.mw;
+  return true;
 }
 
 __device__ __forceinline__ float mix_one(int mode, float a, float b) {

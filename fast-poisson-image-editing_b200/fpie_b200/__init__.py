@@ -13,5 +13,5 @@ fails loudly (RuntimeError / ImportError) otherwise -- there is no CPU path.
 __version__ = "0.1.0"
 
 from .solver import EquSolver, GridSolver, device_count, device_info  # noqa: F401
-from .process import EquProcessor, GridProcessor  # noqa: F401
+from .process import BatchGridProcessor, EquProcessor, GridProcessor  # noqa: F401
 from .register import register  # noqa: F401

@@ -28,6 +28,7 @@ SIGNATURES = {
     "fpie_b200_grid_destroy": [c_void_p],
     "fpie_b200_grid_reset": [c_void_p, c_int, c_int, i32p, c_i64, c_i64, f32p, f32p],
     "fpie_b200_grid_step": [c_void_p, c_int, u8p, f32p],
+    "fpie_b200_grid_step_into": [c_void_p, c_int, u8p, c_i64, f32p],
     "fpie_b200_grid_state": [c_void_p, f32p],
     "fpie_b200_grid_sweeps_async": [c_void_p, c_int],
     "fpie_b200_grid_finish_async": [c_void_p],
@@ -36,6 +37,7 @@ SIGNATURES = {
     "fpie_b200_grid_info": [c_void_p, i64p, i64p, intp, i64p, i64p],
     "fpie_b200_grid_reset_from_images": [c_void_p, u8p, c_int, c_int, u8p, c_int, c_int, c_int, u8p, c_int, c_int,
                                          c_int, c_int, c_int, c_int, c_int, i64p, i32p],
+    "fpie_b200_grid_reset_batch": [c_void_p, u8p, u8p, u8p, c_int, c_int, c_int, c_int, c_int],
     "fpie_b200_grid_reset_slab": [c_void_p, u8p, u8p, u8p, c_int, c_int, c_int, c_int],
     "fpie_b200_grid_band_view": [c_void_p, c_int, P(c_void_p), i64p, i64p, intp, intp],
     "fpie_b200_grid_band_current": [c_void_p, intp],

@@ -90,6 +90,24 @@ class GridProcessor(BaseProcessor):
         return n
 
     def step(self, iteration: int):
-        img, err = self.core.step(iteration)
-        self.tgt[self.x0 : self.x1, self.y0 : self.y1] = img  # process.py:393
+        # process.py:393 `self.tgt[x0:x1, y0:y1] = tgt`, done by the device-to-host copy itself
+        err = self.core.step_into(iteration, self.tgt, self.x0, self.y0)
         return self.tgt, err
+
+
+class BatchGridProcessor(BaseProcessor):
+    """Many small, independent edits at once (the GUI's reset + step per click,
+    fpie/gui.py:96-99, batched): ``reset`` takes stacks of images, ``step``
+    returns the blended stack and one ``err`` triple per edit."""
+
+    def __init__(self, gradient: str = "max", backend: str = BACKEND, device: int | None = None, block_k: int = 0):
+        super().__init__(gradient, backend, GridSolver(8, 8, device=device, block_k=block_k))
+
+    def reset(self, src, mask, tgt) -> int:
+        """``src``, ``tgt``: uint8 ``[B, rows, cols, 3]``; ``mask``: uint8 ``[B, rows, cols]``;
+        the mask of edit ``b`` applies at offset (0, 0) of ``src[b]`` and ``tgt[b]``."""
+        self.core.reset_batch(src, mask, tgt, self.gradient)
+        return int(np.prod(np.asarray(src).shape[:3]))
+
+    def step(self, iteration: int):
+        return self.core.step(iteration)

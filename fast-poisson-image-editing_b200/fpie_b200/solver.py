@@ -115,19 +115,39 @@ class GridSolver(_Handle):
         _lib.check(self._lib.fpie_b200_grid_reset(self.handle, n, w, _ptr(m, ctypes.c_int32), m.strides[0] // 4, 1,
                                                   _ptr(t, ctypes.c_float), _ptr(g, ctypes.c_float)))
         self.shape = (n, w)
+        self.batch_shape = None
 
     def sync(self) -> None:
         """No-op in the reference for every backend but mpi (base_solver.h:142)."""
 
     def step(self, iteration: int):
-        n, w = self._need_shape()
-        img = np.empty((n, w, 3), np.uint8)
-        err = np.empty(3, np.float32)
+        if self.shape is None and getattr(self, "batch_shape", None):
+            b, n, w = self.batch_shape
+            img = np.empty((b, n, w, 3), np.uint8)
+            err = np.empty((b, 3), np.float32)
+        else:
+            n, w = self._need_shape()
+            img = np.empty((n, w, 3), np.uint8)
+            err = np.empty(3, np.float32)
         _lib.check(self._lib.fpie_b200_grid_step(self.handle, int(iteration), _ptr(img, ctypes.c_uint8),
                                                  _ptr(err, ctypes.c_float)))
         return img, err
 
     # -- extras ---------------------------------------------------------------
+    def step_into(self, iteration: int, canvas: np.ndarray, x0: int, y0: int) -> np.ndarray:
+        """``step`` whose uint8 result lands directly in ``canvas[x0:x0+n, y0:y0+m]``
+        (a C-contiguous uint8 ``[rows, cols, 3]`` image); returns ``err``."""
+        n, w = self._need_shape()
+        if canvas.dtype != np.uint8 or canvas.ndim != 3 or canvas.shape[2] != 3 or not canvas.flags["C_CONTIGUOUS"]:
+            raise ValueError("canvas must be a C-contiguous uint8 [rows, cols, 3] image")
+        if x0 < 0 or y0 < 0 or x0 + n > canvas.shape[0] or y0 + w > canvas.shape[1]:
+            raise ValueError("the solved crop does not fit into the canvas")
+        view = canvas[x0 : x0 + n, y0 : y0 + w]
+        err = np.empty(3, np.float32)
+        _lib.check(self._lib.fpie_b200_grid_step_into(self.handle, int(iteration), _ptr(view, ctypes.c_uint8),
+                                                      canvas.strides[0], _ptr(err, ctypes.c_float)))
+        return err
+
     def reset_from_images(self, src, mask, tgt, mask_on_src, mask_on_tgt, gradient: str = "max"):
         """Fused ``GridProcessor.reset`` on the device (fpie/process.py:321-386).
         Returns ``(n_vars, (x0, x1, y0, y1))`` with the box in target coordinates."""
@@ -141,6 +161,24 @@ class GridSolver(_Handle):
             _ptr(box, ctypes.c_int32)))
         self.shape = (int(box[1] - box[0]), int(box[3] - box[2]))
         return int(out_n.value), tuple(int(v) for v in box)
+
+    def reset_batch(self, src, mask, tgt, gradient: str = "max") -> None:
+        """Batched small edits: ``src`` / ``tgt`` uint8 ``[B, rows, cols, 3]``, ``mask`` uint8
+        ``[B, rows, cols]`` (or ``[B, rows, cols, 1|3]``).  Afterwards ``step`` returns
+        ``(uint8 [B, rows, cols, 3], err [B, 3])``."""
+        s = np.ascontiguousarray(src, dtype=np.uint8)
+        t = np.ascontiguousarray(tgt, dtype=np.uint8)
+        mk = np.ascontiguousarray(mask, dtype=np.uint8)
+        if mk.ndim == 3:
+            mk = mk[..., None]
+        if s.ndim != 4 or s.shape[3] != 3 or t.shape != s.shape or mk.shape[:3] != s.shape[:3] or mk.shape[3] not in (1, 3):
+            raise ValueError("expected src/tgt [B, rows, cols, 3] and mask [B, rows, cols(, 1|3)]")
+        b, n, w = s.shape[:3]
+        _lib.check(self._lib.fpie_b200_grid_reset_batch(
+            self.handle, _ptr(s, ctypes.c_uint8), _ptr(mk, ctypes.c_uint8), _ptr(t, ctypes.c_uint8), b, n, w,
+            mk.shape[3], GRAD_CODE[gradient]))
+        self.shape = None
+        self.batch_shape = (b, n, w)
 
     def reset_slab(self, src, mask, tgt, gradient: str = "max") -> None:
         """Load one slab of a row-band sharded problem (see ``fpie_b200.band``): three
@@ -158,6 +196,20 @@ class GridSolver(_Handle):
         out = np.empty((n, w, 3), np.float32)
         _lib.check(self._lib.fpie_b200_grid_state(self.handle, _ptr(out, ctypes.c_float)))
         return out
+
+    def batch_state(self) -> np.ndarray:
+        """fp32 state of a batched solve as ``[B, rows, cols, 3]`` (de-mosaicked on the host)."""
+        if not getattr(self, "batch_shape", None):
+            raise RuntimeError("batch_state needs reset_batch")
+        b, n, w = self.batch_shape
+        bcols = 1
+        while bcols * w < 4096 and bcols < b:  # mosaic rule of GridSolver::reset_batch (csrc/grid.cu)
+            bcols *= 2
+        brows = -(-b // bcols)
+        out = np.empty((brows * n, bcols * w, 3), np.float32)
+        _lib.check(self._lib.fpie_b200_grid_state(self.handle, _ptr(out, ctypes.c_float)))
+        tiles = out.reshape(brows, n, bcols, w, 3).transpose(0, 2, 1, 3, 4).reshape(brows * bcols, n, w, 3)
+        return np.ascontiguousarray(tiles[:b])
 
     def sweeps_async(self, iteration: int) -> None:
         _lib.check(self._lib.fpie_b200_grid_sweeps_async(self.handle, int(iteration)))

@@ -82,6 +82,11 @@ int fpie_b200_grid_reset(fpie_b200_grid *g, int n, int m, const int32_t *mask, i
  * Blocks until the results are in the host buffers. */
 int fpie_b200_grid_step(fpie_b200_grid *g, int iters, uint8_t *out_img, float *out_err3);
 
+/* step() writing the uint8 crop straight into a larger host image: row r of
+ * the result goes to dst + r * dst_row_stride (bytes).  This is the Processor's
+ * paste `tgt[x0:x1, y0:y1] = img` (fpie/process.py:393) done by the copy engine. */
+int fpie_b200_grid_step_into(fpie_b200_grid *g, int iters, uint8_t *dst, int64_t dst_row_stride, float *out_err3);
+
 /* The fp32 state [n, m, 3] (the reference never exposes it from native
  * cores; needed for the fp32 parity check). */
 int fpie_b200_grid_state(fpie_b200_grid *g, float *out_state);
@@ -108,6 +113,15 @@ int fpie_b200_grid_info(fpie_b200_grid *g, int64_t *unknowns, int64_t *launches,
 int fpie_b200_grid_reset_from_images(fpie_b200_grid *g, const uint8_t *src, int sh, int sw, const uint8_t *mask,
                                      int mh, int mw, int mc, const uint8_t *tgt, int th, int tw, int h0, int w0,
                                      int h1, int w1, int grad_mode, int64_t *out_n, int32_t *out_box4);
+
+/* Batched small edits: `batch` independent blends of identical size, src / tgt
+ * uint8 [batch, rows, cols, 3] and mask uint8 [batch, rows, cols, mask_channels]
+ * (cols a multiple of 4).  Each patch is its own grid (no bounding-box crop, its
+ * 1-pixel frame is fixed); the patches are laid out as one mosaic on the device
+ * and swept together.  After this reset, fpie_b200_grid_step / _fetch return
+ * out_img as uint8 [batch, rows, cols, 3] and out_err3 as float [batch, 3]. */
+int fpie_b200_grid_reset_batch(fpie_b200_grid *g, const uint8_t *src, const uint8_t *mask, const uint8_t *tgt, int batch,
+                               int rows, int cols, int mask_channels, int grad_mode);
 
 /* ---- row-band sharding (multi-GPU GridSolver) ----------------------------
  * One solver per GPU holds one slab = a band of rows of the global grid plus
