@@ -1,6 +1,7 @@
 // Upload + mask canonicalisation + bounding box for the fused resets.
 // Follows fpie/process.py:209-224 (Equ) == :338-351 (Grid).
 
+#include <algorithm>
 #include <climits>
 
 #include "prep.cuh"
@@ -8,27 +9,45 @@
 namespace fpie {
 
 // box = {min row, max row, min col, max col} of the canonical mask.
-__global__ void mask_bbox_kernel(BlendImages b, int *__restrict__ box) {
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+// Grid-stride over pixels; warp shuffle reduction, then one set of atomics per CTA.
+__global__ void __launch_bounds__(256) mask_bbox_kernel(BlendImages b, int *__restrict__ box) {
   const long long total = (long long)b.mh * b.mw;
-  int r = 0, c = 0;
-  bool on = false;
-  if (idx < total) {
-    r = (int)(idx / b.mw);
-    c = (int)(idx % b.mw);
-    on = canonical_mask_at(b, r, c);
+  int rmin = INT_MAX, rmax = INT_MIN, cmin = INT_MAX, cmax = INT_MIN;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / b.mw), c = (int)(idx % b.mw);
+    if (canonical_mask_at(b, r, c)) {
+      rmin = min(rmin, r);
+      rmax = max(rmax, r);
+      cmin = min(cmin, c);
+      cmax = max(cmax, c);
+    }
   }
-  const unsigned active = __ballot_sync(0xffffffffu, on);
-  if (!active) return;
-  const int rmin = __reduce_min_sync(0xffffffffu, on ? r : INT_MAX);
-  const int rmax = __reduce_max_sync(0xffffffffu, on ? r : INT_MIN);
-  const int cmin = __reduce_min_sync(0xffffffffu, on ? c : INT_MAX);
-  const int cmax = __reduce_max_sync(0xffffffffu, on ? c : INT_MIN);
-  if ((threadIdx.x & 31) == 0) {
-    atomicMin(&box[0], rmin);
-    atomicMax(&box[1], rmax);
-    atomicMin(&box[2], cmin);
-    atomicMax(&box[3], cmax);
+  rmin = __reduce_min_sync(0xffffffffu, rmin);
+  rmax = __reduce_max_sync(0xffffffffu, rmax);
+  cmin = __reduce_min_sync(0xffffffffu, cmin);
+  cmax = __reduce_max_sync(0xffffffffu, cmax);
+  __shared__ int part[4][8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) {
+    part[0][w] = rmin;
+    part[1][w] = rmax;
+    part[2][w] = cmin;
+    part[3][w] = cmax;
+  }
+  __syncthreads();
+  if (w == 0) {
+    const bool in = lane < (int)(blockDim.x >> 5);
+    rmin = __reduce_min_sync(0xffffffffu, in ? part[0][lane] : INT_MAX);
+    rmax = __reduce_max_sync(0xffffffffu, in ? part[1][lane] : INT_MIN);
+    cmin = __reduce_min_sync(0xffffffffu, in ? part[2][lane] : INT_MAX);
+    cmax = __reduce_max_sync(0xffffffffu, in ? part[3][lane] : INT_MIN);
+    if (lane == 0 && rmin <= rmax) {
+      atomicMin(&box[0], rmin);
+      atomicMax(&box[1], rmax);
+      atomicMin(&box[2], cmin);
+      atomicMax(&box[3], cmax);
+    }
   }
 }
 
@@ -105,7 +124,7 @@ void BlendUpload::upload(cudaStream_t stream, const uint8_t *src, int sh, int sw
     return;
   }
   const long long total = (long long)mh * mw;
-  mask_bbox_kernel<<<(int)ceil_div(total, 256), 256, 0, stream>>>(b, box_.ptr);
+  mask_bbox_kernel<<<(int)std::min<long long>(ceil_div(total, 256), 148 * 16), 256, 0, stream>>>(b, box_.ptr);
   CUDA_CHECK(cudaGetLastError());
   int box[4];
   CUDA_CHECK(cudaMemcpyAsync(box, box_.ptr, sizeof(box), cudaMemcpyDeviceToHost, stream));
