@@ -8,7 +8,7 @@ stale neighbours in between and the result is not Jacobi.  Here every band keeps
 (band + halos) and then refreshes the halo rows from the neighbours' band
 edges: after ``s <= halo`` sweeps only the outer ``s`` halo rows are stale, the
 band itself is exact, so the sharded result equals single-device Jacobi bit for
-bit (modelled in ``oracle/np_oracle.grid_sweeps_banded``).
+bit (the test-suite carries a numpy model of exactly this scheme).
 
 ``BandGridSolver`` is transport- and device-agnostic host logic: the per-rank
 compute object ("core") and the process group are injected, which is how the
