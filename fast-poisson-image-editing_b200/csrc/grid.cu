@@ -281,16 +281,22 @@ __device__ __forceinline__ void tile_sweep_split(float4 (&x)[R], const float4 (&
   if (lane == 0) mbar_arrive(&mail_bar[parity]);
   const float4 first_old = x[1];
   float4 prev = x[0];
+  float4 up, dn;
+  // the neighbours' rows are pulled a few interior rows before they are needed, so that the
+  // barrier check and the shared-memory latency hide behind the remaining interior rows
+  constexpr int PULL_ROW = (R >= 8) ? R - 4 : R - 2;
 #pragma unroll
   for (int i = 1; i < R - 1; ++i) {
+    if (i == PULL_ROW) {
+      mbar_wait(&mail_bar[parity], (mphase >> parity) & 1u);
+      mphase ^= 1u << parity;
+      up = (w > 0) ? mailbox[parity][1][w - 1][lane] : x[0];
+      dn = (w + 1 < NW) ? mailbox[parity][0][w + 1][lane] : x[R - 1];
+    }
     const float4 cur = x[i];
     row_update<MIXED>(x[i], h[i], prev, x[i + 1], mb[i / 8] >> ((i % 8) * 4));
     prev = cur;
   }
-  mbar_wait(&mail_bar[parity], (mphase >> parity) & 1u);
-  mphase ^= 1u << parity;
-  const float4 up = (w > 0) ? mailbox[parity][1][w - 1][lane] : x[0];
-  const float4 dn = (w + 1 < NW) ? mailbox[parity][0][w + 1][lane] : x[R - 1];
   row_update<MIXED>(x[0], h[0], up, first_old, mb[0]);
   row_update<MIXED>(x[R - 1], h[R - 1], prev, dn, mb[(R - 1) / 8] >> (((R - 1) % 8) * 4));
 }

@@ -41,8 +41,8 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    os.makedirs(OBJ_DIR, exist_ok=True)
+def build(force: bool = False, verbose: bool = False, defines=(), lib_path: str = LIB_PATH, obj_dir: str = OBJ_DIR) -> str:
+    os.makedirs(obj_dir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(INCLUDE, "fpie_b200.h"))
     nvcc = _nvcc()
@@ -50,10 +50,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src in SOURCES:
         path = os.path.join(CSRC, src)
-        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [path, *headers]):
-            cmd = [nvcc, *ARCH, *NVCC_FLAGS, "-c", path, "-o", obj]
+            cmd = [nvcc, *ARCH, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", path, "-o", obj]
             log = open(obj + ".log", "w")
             procs.append((src, subprocess.Popen(cmd, stdout=log, stderr=subprocess.STDOUT), log))
     failed = []
@@ -67,10 +67,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
             failed.append(src)
     if failed:
         raise RuntimeError(f"nvcc failed for {failed}")
-    if force or procs or _stale(LIB_PATH, objs):
-        cmd = [nvcc, *ARCH, "-shared", "-o", LIB_PATH, *objs, "-lcudart"]
+    if force or procs or _stale(lib_path, objs):
+        cmd = [nvcc, *ARCH, "-shared", "-o", lib_path, *objs, "-lcudart"]
         subprocess.check_call(cmd)
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":

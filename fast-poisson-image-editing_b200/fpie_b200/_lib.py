@@ -11,7 +11,8 @@ import ctypes
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libfpie_b200.so")
+# FPIE_B200_LIB points tools/ at an experimental build of the same library (never a different implementation)
+LIB_PATH = os.environ.get("FPIE_B200_LIB") or os.path.join(PKG_DIR, "libfpie_b200.so")
 
 c_int = ctypes.c_int
 c_i64 = ctypes.c_int64
