@@ -372,8 +372,9 @@ def run_single(args, work, name):
             "sweeps_per_step": iters,
             "block_k": k,
             "tiles": [info0.get("active_tiles"), info0.get("total_tiles")] if is_grid else None,
-            "l2": "state + gradient planes (>=400 MB) exceed the 126 MB L2; no flush needed" if size >= 4096
-            else "working set fits L2 (L2-resident configuration)",
+            "l2": (f"working set {unknowns * per_update / 1e6:.0f} MB per sweep exceeds the 126 MB L2; no flush needed"
+                   if unknowns * per_update > 2 * 126e6 else
+                   "working set fits the 126 MB L2 (L2-resident configuration; reported separately from the HBM runs)"),
             "reset_s": reset_s,
         },
         "roofline": roofline,

@@ -201,3 +201,27 @@ def test_large_irregular_mask():
     n0, A0, X0, B0, _ = np_oracle.equ_system(src, mask, tgt, (0, 0), (0, 0), "avg")
     np.testing.assert_array_equal(A, A0)
     np.testing.assert_array_equal(B, B0)
+
+
+def test_config3_full_size_ring():
+    """BASELINE config 3 size: 8192^2 ring mask (about 35 M unknowns), grad avg.  The device-built
+    system must equal the oracle's, and 12 gather sweeps must match the C restatement bit for bit."""
+    import fpie_b200
+    from fpie_b200 import synth
+
+    src, mask, tgt = synth.make_problem("ring", 8192, 8192, seed=0)
+    proc = fpie_b200.EquProcessor("avg", "b200")
+    n = proc.reset(src, mask, tgt, (0, 0), (0, 0))
+    assert n > 35_000_000
+    A, X, B = proc.core.system()
+    # ids are row-major: left / right neighbours are i-1 / i+1 wherever they are masked
+    assert ((A[1:, 2] == 0) | (A[1:, 2] == np.arange(1, n) - 1)).all()
+    assert ((A[1:, 3] == 0) | (A[1:, 3] == np.arange(1, n) + 1)).all()
+    out, err = proc.step(12)
+    want = c_oracle.equ_sweeps(A, X, B, 12)
+    np.testing.assert_array_equal(proc.core.state(), want)
+    np.testing.assert_allclose(err, c_oracle.equ_residual(A, want, B)[1], rtol=ERR_RTOL)
+    # the scatter put every solved pixel where the mask is and left the rest of the target alone
+    m_full, _ = np_oracle.canonical_mask(mask)
+    assert np.array_equal(out[m_full == 0], tgt[m_full == 0])
+    assert np.array_equal(out[m_full != 0], c_oracle.clip_u8(want)[1:])
