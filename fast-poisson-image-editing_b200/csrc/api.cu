@@ -229,6 +229,11 @@ API int fpie_b200_equ_step_paste(fpie_b200_equ *e, int iters, uint8_t *out_crop,
   NEED(e);
   return guarded([&] { e->impl.step_paste(iters, out_crop, out_err3); });
 }
+API int fpie_b200_equ_step_paste_into(fpie_b200_equ *e, int iters, uint8_t *dst, int64_t dst_row_stride,
+                                      float *out_err3) {
+  NEED(e);
+  return guarded([&] { e->impl.step_paste(iters, dst, out_err3, dst_row_stride); });
+}
 API int fpie_b200_equ_system(fpie_b200_equ *e, int32_t *out_A, float *out_X, float *out_B) {
   NEED(e);
   return guarded([&] { e->impl.system(out_A, out_X, out_B); });

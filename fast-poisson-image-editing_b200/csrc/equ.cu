@@ -441,7 +441,7 @@ void EquSolver::step(int iters, uint8_t *out_img, float *out_err3) {
   fetch(out_img, out_err3);
 }
 
-void EquSolver::step_paste(int iters, uint8_t *out_crop, float *out_err3) {
+void EquSolver::step_paste(int iters, uint8_t *out_crop, float *out_err3, int64_t row_stride) {
   require_ready();
   FPIE_REQUIRE(fused_, "step_paste needs a solver reset with reset_from_images");
   DeviceGuard guard(device_);
@@ -454,8 +454,12 @@ void EquSolver::step_paste(int iters, uint8_t *out_crop, float *out_err3) {
   CUDA_CHECK(cudaGetLastError());
   stats_.launches += 2;
   CUDA_CHECK(cudaMemcpyAsync(host_err_, err_.ptr, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  const size_t row_bytes = (size_t)crop_m_ * 3;
+  if (row_stride <= 0) row_stride = (int64_t)row_bytes;
+  FPIE_REQUIRE((size_t)row_stride >= row_bytes, "step_paste: destination row stride is smaller than a row");
   if (out_crop)
-    CUDA_CHECK(cudaMemcpyAsync(out_crop, canvas_.ptr, (size_t)crop_n_ * crop_m_ * 3, cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaMemcpy2DAsync(out_crop, (size_t)row_stride, canvas_.ptr, row_bytes, row_bytes, crop_n_,
+                                 cudaMemcpyDeviceToHost, stream_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));
   if (out_err3)
     for (int c = 0; c < 3; ++c) out_err3[c] = (float)host_err_[c];

@@ -57,6 +57,7 @@ SIGNATURES = {
     "fpie_b200_equ_reset_from_images": [c_void_p, u8p, c_int, c_int, u8p, c_int, c_int, c_int, u8p, c_int, c_int,
                                         c_int, c_int, c_int, c_int, c_int, i64p, i32p],
     "fpie_b200_equ_step_paste": [c_void_p, c_int, u8p, f32p],
+    "fpie_b200_equ_step_paste_into": [c_void_p, c_int, u8p, c_i64, f32p],
     "fpie_b200_equ_system": [c_void_p, i32p, f32p, f32p],
 }
 

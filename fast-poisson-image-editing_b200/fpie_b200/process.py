@@ -16,6 +16,8 @@ include/fpie_b200.h).
 
 from __future__ import annotations
 
+import threading
+
 import numpy as np
 
 from .solver import EquSolver, GridSolver
@@ -42,6 +44,23 @@ class BaseProcessor:
     def sync(self) -> None:
         self.core.sync()
 
+    def _reset_with_canvas(self, tgt, device_reset):
+        """Run the device-side reset while a worker thread makes the Processor's private copy of
+        the target (process.py:268 / 384); both release the GIL, so they overlap."""
+        box = {}
+
+        def copy():
+            box["tgt"] = np.array(tgt, dtype=np.uint8, copy=True)
+
+        worker = threading.Thread(target=copy)
+        worker.start()
+        try:
+            result = device_reset()
+        finally:
+            worker.join()
+        self.tgt = box["tgt"]
+        return result
+
     @staticmethod
     def _check_images(src, mask, tgt):
         for name, img in (("src", src), ("tgt", tgt)):
@@ -61,15 +80,16 @@ class EquProcessor(BaseProcessor):
     def reset(self, src, mask, tgt, mask_on_src=(0, 0), mask_on_tgt=(0, 0)) -> int:
         src, mask, tgt = np.asarray(src), np.asarray(mask), np.asarray(tgt)
         self._check_images(src, mask, tgt)
-        n, box = self.core.reset_from_images(src, mask, tgt, mask_on_src, mask_on_tgt, self.gradient)
+        n, box = self._reset_with_canvas(
+            tgt, lambda: self.core.reset_from_images(src, mask, tgt, mask_on_src, mask_on_tgt, self.gradient))
         self.box = box
-        self.tgt = np.array(tgt, dtype=np.uint8, copy=True)  # process.py:268
         return n
 
     def step(self, iteration: int):
-        crop, err = self.core.step_paste(iteration)
-        x0, x1, y0, y1 = self.box
-        self.tgt[x0:x1, y0:y1] = crop  # pixels outside the mask already hold the target
+        # process.py:278 `self.tgt[self.tgt_index] = x[1:]`: the device scatters the K solved pixels into
+        # its copy of the crop, the device-to-host copy lands it in self.tgt[x0:x1, y0:y1]
+        x0, _, y0, _ = self.box
+        err = self.core.step_paste_into(iteration, self.tgt, x0, y0)
         return self.tgt, err
 
 
@@ -84,9 +104,9 @@ class GridProcessor(BaseProcessor):
     def reset(self, src, mask, tgt, mask_on_src=(0, 0), mask_on_tgt=(0, 0)) -> int:
         src, mask, tgt = np.asarray(src), np.asarray(mask), np.asarray(tgt)
         self._check_images(src, mask, tgt)
-        n, box = self.core.reset_from_images(src, mask, tgt, mask_on_src, mask_on_tgt, self.gradient)
+        n, box = self._reset_with_canvas(
+            tgt, lambda: self.core.reset_from_images(src, mask, tgt, mask_on_src, mask_on_tgt, self.gradient))
         self.x0, self.x1, self.y0, self.y1 = box
-        self.tgt = np.array(tgt, dtype=np.uint8, copy=True)  # process.py:384
         return n
 
     def step(self, iteration: int):

@@ -341,6 +341,21 @@ class EquSolver(_Handle):
                                                       _ptr(err, ctypes.c_float)))
         return crop, err
 
+    def step_paste_into(self, iteration: int, canvas: np.ndarray, x0: int, y0: int) -> np.ndarray:
+        """``step_paste`` landing directly in ``canvas[x0:x0+n, y0:y0+m]`` (C-contiguous uint8 image)."""
+        if self.crop_shape is None:
+            raise RuntimeError("step_paste_into needs reset_from_images")
+        n, w = self.crop_shape
+        if canvas.dtype != np.uint8 or canvas.ndim != 3 or canvas.shape[2] != 3 or not canvas.flags["C_CONTIGUOUS"]:
+            raise ValueError("canvas must be a C-contiguous uint8 [rows, cols, 3] image")
+        if x0 < 0 or y0 < 0 or x0 + n > canvas.shape[0] or y0 + w > canvas.shape[1]:
+            raise ValueError("the solved crop does not fit into the canvas")
+        view = canvas[x0 : x0 + n, y0 : y0 + w]
+        err = np.empty(3, np.float32)
+        _lib.check(self._lib.fpie_b200_equ_step_paste_into(self.handle, int(iteration), _ptr(view, ctypes.c_uint8),
+                                                           canvas.strides[0], _ptr(err, ctypes.c_float)))
+        return err
+
     def state(self) -> np.ndarray:
         self._need_reset()
         out = np.empty((self.N, 3), np.float32)

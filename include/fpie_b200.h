@@ -195,6 +195,9 @@ int fpie_b200_equ_reset_from_images(fpie_b200_equ *e, const uint8_t *src, int sh
  * the target's pixels outside the mask.  Only valid after
  * fpie_b200_equ_reset_from_images. */
 int fpie_b200_equ_step_paste(fpie_b200_equ *e, int iters, uint8_t *out_crop, float *out_err3);
+/* Same, writing the crop straight into a larger host image (row r at dst + r * dst_row_stride bytes):
+ * the Processor's `tgt[tgt_index] = x[1:]` (process.py:278) without a host-side pass. */
+int fpie_b200_equ_step_paste_into(fpie_b200_equ *e, int iters, uint8_t *dst, int64_t dst_row_stride, float *out_err3);
 /* Read back the system built by reset_from_images (parity checks). */
 int fpie_b200_equ_system(fpie_b200_equ *e, int32_t *out_A, float *out_X, float *out_B);
 
