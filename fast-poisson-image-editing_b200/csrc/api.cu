@@ -177,6 +177,10 @@ API int fpie_b200_equ_create(int device, void *stream, int block_size, fpie_b200
 API int fpie_b200_equ_destroy(fpie_b200_equ *e) {
   return guarded([&] { delete e; });
 }
+API int fpie_b200_equ_set_mode(fpie_b200_equ *e, int mode) {
+  NEED(e);
+  return guarded([&] { e->impl.set_mode(mode); });
+}
 API int fpie_b200_equ_partition(fpie_b200_equ *e, int n, int m, const int32_t *mask, int64_t mask_row_stride,
                                 int64_t mask_col_stride, int32_t *out_ids) {
   NEED(e);

@@ -149,6 +149,48 @@ equ_sweep_kernel(long long N, long long pitch, const int4 *__restrict__ A, const
   }
 }
 
+// Red-black Gauss-Seidel half-sweep, in place over ids [lo, hi) (fpie/core/openmp/equ.cc:67-80, 109-118).
+// With ids from the red-black partition every neighbour of an updated unknown has the other
+// colour, so the in-place update is race-free and thread-count independent.
+__global__ void __launch_bounds__(1024)
+equ_rb_half_kernel(long long lo, long long hi, long long pitch, const int4 *__restrict__ A,
+                   const float *__restrict__ B, float *__restrict__ x) {
+  const long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= hi) return;
+  const int4 a = A[i];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    float *xc = x + ch * pitch;
+    float s = __fadd_rn(B[ch * pitch + i], xc[a.x]);
+    s = __fadd_rn(s, xc[a.y]);
+    s = __fadd_rn(s, xc[a.z]);
+    s = __fadd_rn(s, xc[a.w]);
+    xc[i] = __fmul_rn(s, 0.25f);
+  }
+}
+
+// parity-filtered flags for the red-black partition: out = mask > 0 && ((row + col) & 1) == parity
+__global__ void rb_flags_kernel(const int32_t *__restrict__ mask, long long count, int m, int parity,
+                                int32_t *__restrict__ out) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= count) return;
+  const int r = (int)(idx / m), c = (int)(idx % m);
+  out[idx] = (mask[idx] > 0 && ((r + c) & 1) == parity) ? 1 : 0;
+}
+
+// ids = odd pixel ? odd_rank : n_odd + even_rank   (0 on unmasked pixels, openmp/equ.cc:30-34)
+__global__ void rb_combine_kernel(const int32_t *__restrict__ mask, long long count, int m,
+                                  const int32_t *__restrict__ odd_ids, const int32_t *__restrict__ even_ids,
+                                  int32_t *__restrict__ ids) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= count) return;
+  const int r = (int)(idx / m), c = (int)(idx % m);
+  const int n_odd = odd_ids[count - 1];
+  int v = 0;
+  if (mask[idx] > 0) v = ((r + c) & 1) ? odd_ids[idx] : n_odd + even_ids[idx];
+  ids[idx] = v;
+}
+
 // err[c] = sum_i |((((B + X[up]) + X[down]) + X[left]) + X[right]) - 4 X[i]|   (np_solver.py:42-50)
 __global__ void __launch_bounds__(256)
 equ_residual_kernel(long long N, long long pitch, const int4 *__restrict__ A, const float *__restrict__ B,
@@ -300,6 +342,36 @@ void EquSolver::scan_ids(const int32_t *dev_mask, int64_t count, int32_t *dev_id
   stats_.launches += 3;
 }
 
+// ids of a contiguous device mask [n, m]: row-major running count (Jacobi mode) or the
+// reference OpenMP backend's odd-then-even labelling (red-black mode).  Sets n_mid_.
+void EquSolver::label(const int32_t *dev_mask, int n, int m, int32_t *dev_ids) {
+  const long long count = (long long)n * m;
+  if (mode_ == 0) {
+    scan_ids(dev_mask, count, dev_ids);
+    n_mid_ = 0;
+    return;
+  }
+  rb_tmp_.resize((size_t)count * 3);
+  int32_t *flags = rb_tmp_.ptr, *odd = rb_tmp_.ptr + count, *even = rb_tmp_.ptr + 2 * count;
+  rb_flags_kernel<<<blocks_for(count, 256), 256, 0, stream_>>>(dev_mask, count, m, 1, flags);
+  scan_ids(flags, count, odd);
+  rb_flags_kernel<<<blocks_for(count, 256), 256, 0, stream_>>>(dev_mask, count, m, 0, flags);
+  scan_ids(flags, count, even);
+  rb_combine_kernel<<<blocks_for(count, 256), 256, 0, stream_>>>(dev_mask, count, m, odd, even, dev_ids);
+  CUDA_CHECK(cudaGetLastError());
+  stats_.launches += 3;
+  int32_t n_odd = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&n_odd, odd + (count - 1), 4, cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  n_mid_ = (int64_t)n_odd + 1;
+}
+
+void EquSolver::set_mode(int mode) {
+  FPIE_REQUIRE(mode == 0 || mode == 1, "EquSolver mode must be 0 (Jacobi) or 1 (red-black Gauss-Seidel)");
+  mode_ = mode;
+  ready_ = false;
+}
+
 void EquSolver::partition(int n, int m, const int32_t *mask, int64_t mask_rs, int64_t mask_cs, int32_t *out_ids) {
   FPIE_REQUIRE(n >= 1 && m >= 1 && mask && out_ids, "partition: bad arguments");
   FPIE_REQUIRE(mask_cs == 1 && mask_rs >= m, "partition: mask rows must be contiguous (column stride 1)");
@@ -310,7 +382,7 @@ void EquSolver::partition(int n, int m, const int32_t *mask, int64_t mask_rs, in
   ids_.resize(count);
   CUDA_CHECK(cudaMemcpy2DAsync(istage_.ptr, (size_t)m * 4, mask, (size_t)mask_rs * 4, (size_t)m * 4, n,
                                cudaMemcpyHostToDevice, stream_));
-  scan_ids(istage_.ptr, (int64_t)count, ids_.ptr);
+  label(istage_.ptr, n, m, ids_.ptr);
   CUDA_CHECK(cudaMemcpyAsync(out_ids, ids_.ptr, count * 4, cudaMemcpyDeviceToHost, stream_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));
 }
@@ -364,9 +436,16 @@ void EquSolver::reset_from_images(const uint8_t *src, int sh, int sw, const uint
   canvas_.resize((size_t)count * 3);
   crop_flags_kernel<<<blocks_for(count, 256), 256, 0, stream_>>>(b, istage_.ptr, canvas_.ptr);
   CUDA_CHECK(cudaGetLastError());
-  scan_ids(istage_.ptr, count, ids_.ptr);
+  label(istage_.ptr, b.n, b.m, ids_.ptr);
+  // K = number of masked pixels: the running count of the flags (the crop frame is never masked,
+  // so the last pixel carries the total in Jacobi mode; red-black ids are not monotone -> count again)
   int32_t last = 0;
-  CUDA_CHECK(cudaMemcpyAsync(&last, ids_.ptr + (count - 1), 4, cudaMemcpyDeviceToHost, stream_));
+  if (mode_ == 0) {
+    CUDA_CHECK(cudaMemcpyAsync(&last, ids_.ptr + (count - 1), 4, cudaMemcpyDeviceToHost, stream_));
+  } else {
+    scan_ids(istage_.ptr, count, rb_tmp_.ptr);
+    CUDA_CHECK(cudaMemcpyAsync(&last, rb_tmp_.ptr + (count - 1), 4, cudaMemcpyDeviceToHost, stream_));
+  }
   CUDA_CHECK(cudaStreamSynchronize(stream_));
   const int64_t K = last;
   allocate(K + 1);
@@ -401,6 +480,20 @@ void EquSolver::sweeps_async(int iters) {
   require_ready();
   FPIE_REQUIRE(iters >= 0, "step: negative iteration count");
   DeviceGuard guard(device_);
+  if (mode_ == 1) {
+    // red-black Gauss-Seidel: odd ids [1, n_mid) then even ids [n_mid, N), in place (openmp/equ.cc:107-118)
+    FPIE_REQUIRE(n_mid_ >= 1 && n_mid_ <= N_, "red-black mode needs ids from this solver's partition()");
+    float *x = X_[cur_].ptr;
+    for (int i = 0; i < iters; ++i) {
+      if (n_mid_ > 1)
+        equ_rb_half_kernel<<<blocks_for(n_mid_ - 1, block_), block_, 0, stream_>>>(1, n_mid_, pitch_, A_.ptr, B_.ptr, x);
+      if (N_ > n_mid_)
+        equ_rb_half_kernel<<<blocks_for(N_ - n_mid_, block_), block_, 0, stream_>>>(n_mid_, N_, pitch_, A_.ptr, B_.ptr, x);
+    }
+    stats_.launches += 2 * (int64_t)iters;
+    CUDA_CHECK(cudaGetLastError());
+    return;
+  }
   for (int i = 0; i < iters; ++i) {
     equ_sweep_kernel<<<blocks_for(N_, block_), block_, 0, stream_>>>(N_, pitch_, A_.ptr, B_.ptr, X_[cur_].ptr,
                                                                     X_[cur_ ^ 1].ptr);

@@ -15,6 +15,7 @@ class EquSolver {
   EquSolver(int device, cudaStream_t stream, int block_size);
   ~EquSolver();
 
+  void set_mode(int mode);
   void partition(int n, int m, const int32_t *mask, int64_t mask_rs, int64_t mask_cs, int32_t *out_ids);
   void reset(int64_t N, const int32_t *A, const float *X, const float *B);
   void reset_from_images(const uint8_t *src, int sh, int sw, const uint8_t *mask, int mh, int mw, int mc,
@@ -36,11 +37,15 @@ class EquSolver {
   void allocate(int64_t N);
   // device-side inclusive scan of (mask > 0) over a contiguous device mask
   void scan_ids(const int32_t *dev_mask, int64_t count, int32_t *dev_ids);
+  void label(const int32_t *dev_mask, int n, int m, int32_t *dev_ids);
 
   int device_;
   cudaStream_t stream_;
   int block_;
   bool ready_ = false;
+  int mode_ = 0;        // 0 = Jacobi, 1 = red-black Gauss-Seidel
+  int64_t n_mid_ = 0;   // first even id (red-black mode)
+  DeviceBuffer<int32_t> rb_tmp_;
   int64_t N_ = 0;      // rows including the constant row 0
   int64_t pitch_ = 0;  // floats per channel plane of X / B
   int cur_ = 0;

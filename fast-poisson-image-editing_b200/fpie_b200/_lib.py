@@ -45,6 +45,7 @@ SIGNATURES = {
     "fpie_b200_grid_set_row_window": [c_void_p, c_int, c_int],
     "fpie_b200_equ_create": [c_int, c_void_p, c_int, P(c_void_p)],
     "fpie_b200_equ_destroy": [c_void_p],
+    "fpie_b200_equ_set_mode": [c_void_p, c_int],
     "fpie_b200_equ_partition": [c_void_p, c_int, c_int, i32p, c_i64, c_i64, i32p],
     "fpie_b200_equ_reset": [c_void_p, c_i64, i32p, f32p, f32p],
     "fpie_b200_equ_step": [c_void_p, c_int, u8p, f32p],

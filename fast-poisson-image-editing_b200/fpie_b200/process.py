@@ -74,8 +74,8 @@ class EquProcessor(BaseProcessor):
     """PIE Jacobi equation processor on the b200 core (fpie/process.py:146-280)."""
 
     def __init__(self, gradient: str = "max", backend: str = BACKEND, n_cpu: int = 0, min_interval: int = 100,
-                 block_size: int = 256, device: int | None = None):
-        super().__init__(gradient, backend, EquSolver(block_size, device=device))
+                 block_size: int = 256, device: int | None = None, mode: str = "jacobi"):
+        super().__init__(gradient, backend, EquSolver(block_size, device=device, mode=mode))
 
     def reset(self, src, mask, tgt, mask_on_src=(0, 0), mask_on_tgt=(0, 0)) -> int:
         src, mask, tgt = np.asarray(src), np.asarray(mask), np.asarray(tgt)

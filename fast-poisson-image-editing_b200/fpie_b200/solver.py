@@ -261,14 +261,24 @@ class GridSolver(_Handle):
 class EquSolver(_Handle):
     """Drop-in for ``core_cuda.EquSolver(block_size)`` (fpie/process.py:173-174)."""
 
-    def __init__(self, block_size: int = 256, device: int | None = None):
+    MODES = {"jacobi": 0, "redblack": 1}
+
+    def __init__(self, block_size: int = 256, device: int | None = None, mode: str = "jacobi"):
+        """``mode="redblack"`` selects the reference OpenMP backend's red-black Gauss-Seidel
+        (fpie/core/openmp/equ.cc:22-56, 107-118) instead of true Jacobi; ``partition`` then labels
+        odd pixels before even ones, exactly as ``core_openmp.EquSolver.partition`` does."""
         super().__init__()
+        if mode not in self.MODES:
+            raise ValueError(f"mode must be one of {sorted(self.MODES)}")
         self.device = default_device() if device is None else int(device)
+        self.mode = mode
         self.N = 0
         self.crop_shape = None
         stream = _lib.current_stream_handle(self.device)
         _lib.check(self._lib.fpie_b200_equ_create(self.device, ctypes.c_void_p(stream), int(block_size),
                                                   ctypes.byref(self._h)))
+        if mode != "jacobi":
+            _lib.check(self._lib.fpie_b200_equ_set_mode(self.handle, self.MODES[mode]))
 
     def close(self) -> None:
         if self._h:

@@ -156,6 +156,15 @@ int fpie_b200_grid_set_row_window(fpie_b200_grid *g, int row_lo, int row_hi);
 int fpie_b200_equ_create(int device, void *stream, int block_size, fpie_b200_equ **out);
 int fpie_b200_equ_destroy(fpie_b200_equ *e);
 
+/* Iteration scheme: FPIE_B200_EQU_JACOBI (default; true Jacobi, fpie/np_solver.py:33-41) or
+ * FPIE_B200_EQU_REDBLACK -- the reference OpenMP backend's deterministic red-black Gauss-Seidel:
+ * partition labels odd pixels first, then even ones (fpie/core/openmp/equ.cc:22-56) and a sweep is
+ * two in-place half-sweeps (equ.cc:107-118).  Set before partition / reset; red-black needs the
+ * ids of this solver's own partition (or of reset_from_images). */
+#define FPIE_B200_EQU_JACOBI 0
+#define FPIE_B200_EQU_REDBLACK 1
+int fpie_b200_equ_set_mode(fpie_b200_equ *e, int mode);
+
 /* EquSolver::partition(mask) -> ids (equ.cu:36-54; np_solver.py:14-16):
  * row-major inclusive count of mask > 0, computed by a device prefix scan.
  * mask int32 [n, m] with element strides; ids int32 [n, m] C-contiguous.

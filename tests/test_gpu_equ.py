@@ -225,3 +225,64 @@ def test_config3_full_size_ring():
     m_full, _ = np_oracle.canonical_mask(mask)
     assert np.array_equal(out[m_full == 0], tgt[m_full == 0])
     assert np.array_equal(out[m_full != 0], c_oracle.clip_u8(want)[1:])
+
+
+@pytest.mark.parametrize("name,mode", [("rng24", "max"), ("ring_off", "avg"), ("holes_full", "src"), ("disk_sat", "max")])
+def test_redblack_mode_matches_reference_openmp_scheme(golden, name, mode):
+    """mode="redblack": the reference OpenMP EquSolver's deterministic red-black Gauss-Seidel
+    (openmp/equ.cc:22-56, 107-118) -- ids from the device partition, then bit-exact sweeps."""
+    import fpie_b200
+
+    c = golden_case(golden, name)
+    m_full, (x0, x1, y0, y1) = np_oracle.canonical_mask(c["mask"])
+    crop = m_full[x0:x1, y0:y1]
+    s = fpie_b200.EquSolver(256, mode="redblack")
+    ids = s.partition(crop)
+    want_ids, n_mid = np_oracle.partition_redblack(crop)
+    np.testing.assert_array_equal(ids, want_ids)
+    n, A, X, B, index = np_oracle.equ_system(c["src"], c["mask"], c["tgt"], c["off_src"], c["off_tgt"], mode, ids=ids)
+    s.reset(n, A, X, B)
+    s.step(4)
+    img, err = s.step(7)
+    want = np_oracle.equ_sweeps_redblack(A, X, B, 11, n_mid)
+    np.testing.assert_array_equal(s.state(), want)
+    np.testing.assert_array_equal(img, np_oracle.clip_u8(want))
+    np.testing.assert_allclose(err, np_oracle.equ_residual_f64(A, want, B), rtol=ERR_RTOL, atol=1e-3)
+    ref = c_oracle.load_reference_core("core_openmp")
+    if ref is not None:  # the compiled reference itself, when oracle/_ref travelled to this box
+        r = ref.EquSolver(4)
+        r.partition(np.ascontiguousarray(crop))
+        r.reset(n, A, X, B)
+        rimg, rerr = r.step(11)
+        np.testing.assert_array_equal(img, rimg)
+        np.testing.assert_allclose(err, rerr, rtol=ERR_RTOL, atol=1e-3)
+    # processor level (device-side red-black labelling + build + paste)
+    proc = fpie_b200.EquProcessor(mode, "b200", mode="redblack")
+    assert proc.reset(c["src"], c["mask"], c["tgt"], c["off_src"], c["off_tgt"]) == n
+    A2, X2, B2 = proc.core.system()
+    np.testing.assert_array_equal(A2, A)
+    np.testing.assert_array_equal(B2, B)
+    out, err2 = proc.step(11)
+    canvas = c["tgt"].copy()
+    canvas[index] = np_oracle.clip_u8(want)[1:]
+    np.testing.assert_array_equal(out, canvas)
+
+
+def test_redblack_large_and_errors():
+    import fpie_b200
+    from fpie_b200 import synth
+
+    src, mask, tgt = synth.make_problem("star", 700, 900, seed=4)
+    proc = fpie_b200.EquProcessor("max", "b200", mode="redblack")
+    n = proc.reset(src, mask, tgt, (0, 0), (0, 0))
+    A, X, B = proc.core.system()
+    m_full, (x0, x1, y0, y1) = np_oracle.canonical_mask(mask)
+    _, n_mid = np_oracle.partition_redblack(m_full[x0:x1, y0:y1])
+    proc.step(30)
+    np.testing.assert_array_equal(proc.core.state(), np_oracle.equ_sweeps_redblack(A, X, B, 30, n_mid))
+    with pytest.raises(ValueError):
+        fpie_b200.EquSolver(256, mode="sor")
+    s = fpie_b200.EquSolver(256, mode="redblack")
+    s.reset(n, A, X, B)  # no partition() on this solver: the colour split is unknown
+    with pytest.raises(RuntimeError, match="partition"):
+        s.step(1)

@@ -212,3 +212,30 @@ def test_reference_openmp_grid_medium():
     assert diff.max() <= 1
     _, e64 = c_oracle.grid_residual(mask, state, grad)
     np.testing.assert_allclose(err, e64, rtol=1e-4)
+
+
+def test_redblack_restatement_matches_reference_openmp(golden):
+    """The red-black Gauss-Seidel restatement vs the compiled reference core_openmp.EquSolver
+    (fpie/core/openmp/equ.cc): ids, n_mid behaviour, uint8 output, err."""
+    core = c_oracle.load_reference_core("core_openmp")
+    if core is None:
+        pytest.skip("oracle/_ref/core_openmp not built (needs /root/reference)")
+    for name, mode in (("rng24", "max"), ("ring_off", "avg"), ("holes_full", "src")):
+        c = golden_case(golden, name)
+        m_full, (x0, x1, y0, y1) = np_oracle.canonical_mask(c["mask"])
+        crop = np.ascontiguousarray(m_full[x0:x1, y0:y1])
+        solver = core.EquSolver(3)
+        ref_ids = solver.partition(crop)
+        ids, n_mid = np_oracle.partition_redblack(crop)
+        np.testing.assert_array_equal(ref_ids, ids)
+        n, A, X, B, _ = np_oracle.equ_system(c["src"], c["mask"], c["tgt"], c["off_src"], c["off_tgt"], mode, ids=ids)
+        solver.reset(n, A, X, B)
+        img, err = solver.step(9)
+        want = np_oracle.equ_sweeps_redblack(A, X, B, 9, n_mid)
+        np.testing.assert_array_equal(img, np_oracle.clip_u8(want))
+        np.testing.assert_allclose(err, np_oracle.equ_residual_f64(A, want, B), rtol=1e-5, atol=1e-3)
+        # thread-count independent (deterministic red-black)
+        solver2 = core.EquSolver(1)
+        solver2.partition(crop)
+        solver2.reset(n, A, X, B)
+        np.testing.assert_array_equal(solver2.step(9)[0], img)
