@@ -61,7 +61,7 @@ void BlendUpload::upload_batch(cudaStream_t stream, const uint8_t *src, const ui
                                int batch, int ph, int pw, int mc, int mode, int bcols) {
   FPIE_REQUIRE(src && mask && tgt, "reset_batch: null image");
   FPIE_REQUIRE(batch > 0 && ph > 0 && pw > 0 && bcols > 0, "reset_batch: empty batch");
-  FPIE_REQUIRE(mc == 1 || mc == 3, "reset_batch: mask must have 1 or 3 channels");
+  FPIE_REQUIRE(mc >= 1 && mc <= 16, "reset_batch: mask must have 1..16 channels");
   FPIE_REQUIRE(mode >= 0 && mode <= 2, "reset_batch: unknown gradient mode");
   const size_t px = (size_t)batch * ph * pw;
   src_.resize(px * 3);
@@ -91,7 +91,7 @@ void BlendUpload::upload(cudaStream_t stream, const uint8_t *src, int sh, int sw
                          bool crop) {
   FPIE_REQUIRE(src && mask && tgt, "reset_from_images: null image");
   FPIE_REQUIRE(sh > 0 && sw > 0 && mh > 0 && mw > 0 && th > 0 && tw > 0, "reset_from_images: empty image");
-  FPIE_REQUIRE(mc == 1 || mc == 3, "reset_from_images: mask must have 1 or 3 channels");
+  FPIE_REQUIRE(mc >= 1 && mc <= 16, "reset_from_images: mask must have 1..16 channels");
   FPIE_REQUIRE(mode >= 0 && mode <= 2, "reset_from_images: unknown gradient mode");
   const size_t sbytes = (size_t)sh * sw * 3, mbytes = (size_t)mh * mw * mc, tbytes = (size_t)th * tw * 3;
   src_.resize(sbytes);

@@ -13,7 +13,7 @@ struct BlendImages {
   const uint8_t *mask;
   const uint8_t *tgt;
   int sh, sw;      // source rows / cols
-  int mh, mw, mc;  // mask rows / cols / channels (1 or 3)
+  int mh, mw, mc;  // mask rows / cols / channels (any count >= 1; the reference takes mean(-1))
   int th, tw;      // target rows / cols
   // crop box in mask coordinates and the offsets of mask (0,0) in src / tgt
   int x0, y0, n, m;
@@ -58,7 +58,8 @@ class BlendUpload {
 __device__ __forceinline__ bool canonical_mask_at(const BlendImages &b, int r, int c) {
   if (r <= 0 || c <= 0 || r >= b.mh - 1 || c >= b.mw - 1) return false;
   const uint8_t *p = b.mask + ((long long)r * b.mw + c) * b.mc;
-  const int s = (b.mc == 3) ? (int)p[0] + (int)p[1] + (int)p[2] : (int)p[0];
+  int s = 0;
+  for (int k = 0; k < b.mc; ++k) s += (int)p[k];
   return s >= 128 * b.mc;
 }
 

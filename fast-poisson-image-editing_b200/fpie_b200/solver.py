@@ -45,9 +45,9 @@ def _as_u8_mask(mask) -> np.ndarray:
     a = np.ascontiguousarray(mask, dtype=np.uint8)
     if a.ndim == 2:
         return a[:, :, None]
-    if a.ndim == 3 and a.shape[2] in (1, 3):
-        return a
-    raise ValueError("mask must be uint8 [rows, cols] or [rows, cols, 1|3]")
+    if a.ndim == 3 and 1 <= a.shape[2] <= 16:
+        return a  # any channel count: the reference thresholds mask.mean(-1) (fpie/process.py:209-211)
+    raise ValueError("mask must be uint8 [rows, cols] or [rows, cols, channels]")
 
 
 def default_device() -> int:
@@ -171,7 +171,7 @@ class GridSolver(_Handle):
         mk = np.ascontiguousarray(mask, dtype=np.uint8)
         if mk.ndim == 3:
             mk = mk[..., None]
-        if s.ndim != 4 or s.shape[3] != 3 or t.shape != s.shape or mk.shape[:3] != s.shape[:3] or mk.shape[3] not in (1, 3):
+        if s.ndim != 4 or s.shape[3] != 3 or t.shape != s.shape or mk.shape[:3] != s.shape[:3] or not 1 <= mk.shape[3] <= 16:
             raise ValueError("expected src/tgt [B, rows, cols, 3] and mask [B, rows, cols(, 1|3)]")
         b, n, w = s.shape[:3]
         _lib.check(self._lib.fpie_b200_grid_reset_batch(

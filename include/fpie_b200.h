@@ -106,7 +106,7 @@ int fpie_b200_grid_info(fpie_b200_grid *g, int64_t *unknowns, int64_t *launches,
 /* Fused Processor-level reset (GridProcessor.reset, fpie/process.py:321-386)
  * executed on the device from uint8 images: mask threshold / frame clear /
  * bounding box, crop, mixed gradient, state upload.
- * src [sh, sw, 3], tgt [th, tw, 3], mask [mh, mw, mc] with mc in {1, 3};
+ * src [sh, sw, 3], tgt [th, tw, 3], mask [mh, mw, mc] with any mc in 1..16 (thresholded on the channel mean);
  * (h0, w0) / (h1, w1) = position of mask pixel (0,0) in src / tgt.
  * out_box = {x0, x1, y0, y1} of the solved crop in target coordinates;
  * returns the crop size n*m in *out_n ("# of vars" of the reference). */
