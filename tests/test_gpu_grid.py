@@ -187,6 +187,25 @@ def test_edge_cases():
     assert img[1, 1].tolist() == [0, 0, 255]
 
 
+def test_mask_channel_counts(golden):
+    """The reference thresholds mask.mean(-1) for any channel count (process.py:209-211)."""
+    import fpie_b200
+
+    c = golden_case(golden, "ring_off")
+    base = c["mask"]  # 3 channels with a deliberately skewed middle channel
+    rgba = np.concatenate([base, base[:, :, :1]], axis=2)  # 4 channels
+    gray = base[:, :, 0]
+    for mask in (rgba, gray, gray[:, :, None]):
+        proc = fpie_b200.GridProcessor("avg", "b200")
+        n = proc.reset(c["src"], mask, c["tgt"], c["off_src"], c["off_tgt"])
+        want = np_oracle.GridOracle("avg")
+        assert want.reset(c["src"], mask, c["tgt"], c["off_src"], c["off_tgt"]) == n
+        out, err = proc.step(9)
+        wout, werr = want.step(9)
+        np.testing.assert_array_equal(out, wout)
+        np.testing.assert_allclose(err, werr, rtol=ERR_RTOL)
+
+
 def test_error_behaviour():
     import fpie_b200
 
