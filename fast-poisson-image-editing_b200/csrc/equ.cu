@@ -128,9 +128,43 @@ __global__ void check_index_kernel(long long N, const int4 *__restrict__ A, int 
   if (bad) atomicExch(flag, 1);
 }
 
+// Compact neighbour table for row-major ids: when left / right are always "absent" or i-1 / i+1
+// (true for every system built from a row-major partition) only up / down need to be stored;
+// bit 31 of each carries "left present" / "right present".  16 -> 8 bytes per unknown per sweep.
+__global__ void compact_index_kernel(long long N, const int4 *__restrict__ A, int2 *__restrict__ UD,
+                                     int *__restrict__ unstructured) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int4 a = A[i];
+  const bool ok = (a.z == 0 || a.z == i - 1) && (a.w == 0 || a.w == i + 1);
+  if (!ok) atomicExch(unstructured, 1);
+  UD[i] = make_int2(a.x | (a.z != 0 ? (int)0x80000000 : 0), a.y | (a.w != 0 ? (int)0x80000000 : 0));
+}
+
 // ---------------------------------------------------------------------------
 // sweep / residual / output
 // ---------------------------------------------------------------------------
+// Same update as equ_sweep_kernel, reading the compact table: left / right are the adjacent
+// unknowns i-1 / i+1 (coalesced) or the constant row 0.
+__global__ void __launch_bounds__(1024)
+equ_sweep_lr_kernel(long long N, long long pitch, const int2 *__restrict__ UD, const float *__restrict__ B,
+                    const float *__restrict__ xin, float *__restrict__ xout) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int2 ud = UD[i];
+  const int up = ud.x & 0x7fffffff, dn = ud.y & 0x7fffffff;
+  const long long lf = (ud.x < 0) ? i - 1 : 0, rt = (ud.y < 0) ? i + 1 : 0;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const float *x = xin + ch * pitch;
+    float s = __fadd_rn(B[ch * pitch + i], x[up]);
+    s = __fadd_rn(s, x[dn]);
+    s = __fadd_rn(s, x[lf]);
+    s = __fadd_rn(s, x[rt]);
+    xout[ch * pitch + i] = __fmul_rn(s, 0.25f);
+  }
+}
+
 // X'[i] = ((((B[i] + X[up]) + X[down]) + X[left]) + X[right]) / 4   (np_solver.py:33-41)
 __global__ void __launch_bounds__(1024)
 equ_sweep_kernel(long long N, long long pitch, const int4 *__restrict__ A, const float *__restrict__ B,
@@ -316,6 +350,10 @@ EquSolver::EquSolver(int device, cudaStream_t stream, int block_size) : device_(
   FPIE_REQUIRE(prop.major >= 10, "fpie_b200 is built for sm_100a (Blackwell) only");
   // the reference's -z flag (fpie/args.py block-size, default 1024); we accept
   // any multiple of 32 up to 1024 and default to 256
+  if (block_size >= 100000) {  // 100000 + z: block size z, always the generic int4 table (cross-checks)
+    force_generic_ = true;
+    block_size -= 100000;
+  }
   if (block_size <= 0) block_size = 256;
   block_ = std::min(1024, std::max(32, block_size / 32 * 32));
   err_.resize(3);
@@ -418,7 +456,21 @@ void EquSolver::reset(int64_t N, const int32_t *A, const float *X, const float *
   CUDA_CHECK(cudaStreamSynchronize(stream_));
   FPIE_REQUIRE(*host_flag_ == 0, "EquSolver.reset: A holds an index outside [0, N)");
   stats_.unknowns = N - 1;
+  compact_tables();
   ready_ = true;
+}
+
+void EquSolver::compact_tables() {
+  structured_ = false;
+  if (mode_ != 0) return;
+  ud_.resize((size_t)N_);
+  CUDA_CHECK(cudaMemsetAsync(flag_.ptr, 0, sizeof(int), stream_));
+  compact_index_kernel<<<blocks_for(N_, 256), 256, 0, stream_>>>(N_, A_.ptr, ud_.ptr, flag_.ptr);
+  CUDA_CHECK(cudaGetLastError());
+  stats_.launches += 1;
+  CUDA_CHECK(cudaMemcpyAsync(host_flag_, flag_.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  structured_ = (*host_flag_ == 0) && !force_generic_;
 }
 
 void EquSolver::reset_from_images(const uint8_t *src, int sh, int sw, const uint8_t *mask, int mh, int mw, int mc,
@@ -466,6 +518,7 @@ void EquSolver::reset_from_images(const uint8_t *src, int sh, int sw, const uint
   crop_m_ = b.m;
   fused_ = true;
   stats_.unknowns = K;
+  compact_tables();
   ready_ = true;
   if (out_n) *out_n = K + 1;
   if (out_box4) {
@@ -495,8 +548,12 @@ void EquSolver::sweeps_async(int iters) {
     return;
   }
   for (int i = 0; i < iters; ++i) {
-    equ_sweep_kernel<<<blocks_for(N_, block_), block_, 0, stream_>>>(N_, pitch_, A_.ptr, B_.ptr, X_[cur_].ptr,
-                                                                    X_[cur_ ^ 1].ptr);
+    if (structured_)
+      equ_sweep_lr_kernel<<<blocks_for(N_, block_), block_, 0, stream_>>>(N_, pitch_, ud_.ptr, B_.ptr, X_[cur_].ptr,
+                                                                         X_[cur_ ^ 1].ptr);
+    else
+      equ_sweep_kernel<<<blocks_for(N_, block_), block_, 0, stream_>>>(N_, pitch_, A_.ptr, B_.ptr, X_[cur_].ptr,
+                                                                      X_[cur_ ^ 1].ptr);
     cur_ ^= 1;
   }
   stats_.launches += iters;

@@ -31,6 +31,7 @@ class EquSolver {
   void system(int32_t *out_A, float *out_X, float *out_B);
 
   const EquStats &stats() const { return stats_; }
+  bool structured() const { return structured_; }
 
  private:
   void require_ready() const;
@@ -38,6 +39,7 @@ class EquSolver {
   // device-side inclusive scan of (mask > 0) over a contiguous device mask
   void scan_ids(const int32_t *dev_mask, int64_t count, int32_t *dev_ids);
   void label(const int32_t *dev_mask, int n, int m, int32_t *dev_ids);
+  void compact_tables();
 
   int device_;
   cudaStream_t stream_;
@@ -50,6 +52,9 @@ class EquSolver {
   int64_t pitch_ = 0;  // floats per channel plane of X / B
   int cur_ = 0;
   DeviceBuffer<int4> A_;
+  DeviceBuffer<int2> ud_;      // compact table (up, down, left/right presence bits)
+  bool structured_ = false;    // left/right are always i-1 / i+1 or absent
+  bool force_generic_ = false;
   DeviceBuffer<float> X_[2];
   DeviceBuffer<float> B_;
   DeviceBuffer<float> stage_;

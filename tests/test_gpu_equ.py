@@ -47,7 +47,7 @@ def test_partition_scan_sizes(shape):
     np.testing.assert_array_equal(s.partition(neg), np_oracle.partition_rowmajor(neg))
 
 
-@pytest.mark.parametrize("block", [32, 256, 1024])
+@pytest.mark.parametrize("block", [32, 256, 1024, 100256])  # 100000 + z forces the generic int4 table
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_core_matches_reference_golden(golden, name, block):
     c = golden_case(golden, name)
@@ -286,3 +286,25 @@ def test_redblack_large_and_errors():
     s.reset(n, A, X, B)  # no partition() on this solver: the colour split is unknown
     with pytest.raises(RuntimeError, match="partition"):
         s.step(1)
+
+
+def test_unstructured_ids_use_the_generic_table(golden):
+    """Any bijection of the masked pixels onto 1..K is a legal labelling (process.py:187-190).  A random
+    relabelling breaks the left = i-1 / right = i+1 pattern, so the compact table must not be used --
+    and the result must still be the relabelled Jacobi iterate, bit for bit."""
+    A, X, B = (golden[f"holes_full/equ/max/{k}"] for k in ("A", "X0", "B"))
+    n = A.shape[0]
+    rng = np.random.default_rng(5)
+    perm = np.concatenate([[0], 1 + rng.permutation(n - 1)])  # new id of old id i
+    inv = np.argsort(perm)
+    A2 = perm[A][inv].astype(np.int32)
+    X2, B2 = X[inv], B[inv]
+    s = _solver()
+    s.reset(n, A2, X2, B2)
+    s.step(21)
+    want = np_oracle.equ_sweeps(A, X, B, 21)
+    np.testing.assert_array_equal(s.state(), want[inv])
+    # and the structured path on the original labelling gives the same values
+    s.reset(n, A, X, B)
+    s.step(21)
+    np.testing.assert_array_equal(s.state(), want)
