@@ -194,6 +194,91 @@ class BandGridSolver:
         return getattr(self.core, "torch_device", "cpu")
 
 
+def canonical_crop(mask: np.ndarray):
+    """Host-side mask canonicalisation of the Processor (fpie/process.py:338-351), cheap uint8 work:
+    threshold on the channel mean, clear the 1-pixel frame, bounding box +-1.
+    Returns ``(mask_u8 [rows, cols] with 255 inside, (x0, x1, y0, y1))`` in mask coordinates."""
+    m = np.asarray(mask)
+    if m.ndim == 3:
+        m = m.astype(np.uint16).sum(-1) >= 128 * m.shape[2]  # == mean(-1) >= 128, exactly
+    else:
+        m = m >= 128
+    m = m.copy()
+    m[0, :] = m[-1, :] = False
+    m[:, 0] = m[:, -1] = False
+    rows = np.flatnonzero(m.any(axis=1))
+    cols = np.flatnonzero(m.any(axis=0))
+    if rows.size == 0:
+        raise RuntimeError("reset: the mask is empty after thresholding and clearing its 1-pixel frame")
+    x0, x1, y0, y1 = int(rows[0]) - 1, int(rows[-1]) + 2, int(cols[0]) - 1, int(cols[-1]) + 2
+    return (m[x0:x1, y0:y1].astype(np.uint8) * 255), (x0, x1, y0, y1)
+
+
+class BandGridProcessor:
+    """``GridProcessor`` interface over row bands (one process per GPU).
+
+    The call sequence is the reference's MPI one (fpie/cli.py:34-57 with ``-b mpi``): every rank
+    constructs the processor, ``reset`` is called with the images, ``sync()``, then ``step(n)`` in
+    lock-step on every rank.  Unlike the reference (rank 0 resets, ``sync`` broadcasts the whole fp32
+    problem, mpi/grid.cc:34-54) every rank takes the uint8 images and keeps only its slab; ``step``
+    returns the full blended target on rank 0 and ``None`` elsewhere (process.py:388-395)."""
+
+    def __init__(self, gradient: str = "max", core=None, dist=None, group=None, halo: int = 16):
+        self.gradient = gradient
+        self.solver = BandGridSolver(core, dist, group, halo)
+        self.dist, self.group = dist, group
+        self.rank = self.solver.rank
+        self.root = self.rank == 0
+
+    def reset(self, src, mask, tgt, mask_on_src=(0, 0), mask_on_tgt=(0, 0)) -> int:
+        src, tgt = np.asarray(src), np.asarray(tgt)
+        crop_mask, (x0, x1, y0, y1) = canonical_crop(mask)
+        n, m = crop_mask.shape
+        so = (mask_on_src[0] + x0, mask_on_src[1] + y0)
+        to = (mask_on_tgt[0] + x0, mask_on_tgt[1] + y0)
+        for img, o, what in ((src, so, "source"), (tgt, to, "target")):
+            if o[0] < 0 or o[1] < 0 or o[0] + n > img.shape[0] or o[1] + m > img.shape[1]:
+                raise RuntimeError(f"reset: the mask bounding box falls outside the {what} image")
+        plan = make_plan(n, self.solver.world, self.rank, self.solver.halo)
+        sl = slice(plan.slab_lo, plan.slab_hi)
+        self.solver.reset_slab(
+            n,
+            np.ascontiguousarray(src[so[0] : so[0] + n, so[1] : so[1] + m][sl]),
+            np.ascontiguousarray(crop_mask[sl]),
+            np.ascontiguousarray(tgt[to[0] : to[0] + n, to[1] : to[1] + m][sl]),
+            self.gradient,
+        )
+        self.box = (to[0], to[0] + n, to[1], to[1] + m)
+        self.tgt = np.array(tgt, dtype=np.uint8, copy=True) if self.root else None
+        return n * m
+
+    def sync(self) -> None:
+        self.solver.sync()
+
+    def step(self, iteration: int):
+        import torch
+
+        band, err = self.solver.step(iteration)
+        plan, world = self.solver.plan, self.solver.world
+        off = band_offsets(plan.n_rows, world)
+        m = self.box[3] - self.box[2]
+        dev = self.solver._reduce_device()
+        mine = torch.from_numpy(np.ascontiguousarray(band)).to(dev)
+        # bands have different heights: gather into equal-size padded buffers
+        tallest = max(off[i + 1] - off[i] for i in range(world))
+        padded = torch.zeros((tallest, m, 3), dtype=torch.uint8, device=dev)
+        padded[: mine.shape[0]] = mine
+        parts = [torch.empty_like(padded) for _ in range(world)] if self.root else None
+        self.dist.gather(padded, parts, dst=0, group=self.group)
+        if not self.root:
+            return None
+        x0, _, y0, y1 = self.box
+        for i in range(world):
+            rows = off[i + 1] - off[i]
+            self.tgt[x0 + off[i] : x0 + off[i + 1], y0:y1] = parts[i][:rows].cpu().numpy()
+        return self.tgt, err
+
+
 class _DeviceRows:
     """``__cuda_array_interface__`` window onto solver-owned device memory."""
 

@@ -27,6 +27,17 @@ class OracleBandCore:
         self.planes = np.ascontiguousarray(np.asarray(tgt, np.float32).transpose(2, 0, 1))
         self.window = (0, m.shape[0])
 
+    def reset_slab(self, src, mask, tgt, gradient):
+        """uint8 slab images -> the same grid problem the CUDA slab reset builds: the whole slab is the
+        grid, mask thresholded at 128, gradient from the slab's own pixels, outer frame fixed."""
+        m = (np.asarray(mask).reshape(mask.shape[0], mask.shape[1], -1).mean(-1) >= 128).astype(np.int32)
+        m[0, :] = m[-1, :] = 0
+        m[:, 0] = m[:, -1] = 0
+        n, w = m.shape
+        grad = np_oracle._pixel_gradient(gradient, src, tgt, (0, 0), (0, 0), (n, w))
+        grad[m == 0] = 0
+        self.reset(n * w, m, tgt.astype(np.float32), grad)
+
     def _aos(self):
         return self.planes.transpose(1, 2, 0)
 
@@ -90,6 +101,15 @@ class ThreadDist:
             if op.op == "irecv":
                 op.tensor.copy_(self.q[(op.peer, me)].get(timeout=120))
         return []
+
+    def gather(self, tensor, gather_list=None, dst=0, group=None):
+        me = self.local.rank
+        self.slots[me] = tensor.clone()
+        self.bar.wait()
+        if me == dst:
+            for i, out in enumerate(gather_list):
+                out.copy_(self.slots[i])
+        self.bar.wait()
 
     def all_reduce(self, tensor, group=None):
         me = self.local.rank

@@ -94,3 +94,61 @@ def test_gloo_bands_reproduce_global_jacobi(tmp_path, world, halo, steps):
         np.testing.assert_allclose(z["err"][-1], np_oracle.grid_residual_f64(mask, want, grad), rtol=1e-6)
     assert covered == shape[0]
     np.testing.assert_array_equal(got, want)  # bit-identical to single-domain Jacobi
+
+
+def _proc_worker(rank, world, port, out_dir):
+    for p in (ROOT, PKG_ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from band_helpers import OracleBandCore
+
+    from fpie_b200 import band, synth
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        src, mask, tgt = synth.make_problem("circle", 120, 90, seed=6)
+        big_tgt = np.random.default_rng(1).integers(0, 256, (150, 130, 3), dtype=np.uint8)
+        proc = band.BandGridProcessor("avg", OracleBandCore(), dist, halo=6)
+        n = proc.reset(src, np.repeat(mask[:, :, None], 3, 2), big_tgt, (0, 0), (20, 30))
+        proc.sync()
+        proc.step(10)
+        res = proc.step(13)
+        if rank == 0:
+            out, err = res
+            np.savez(os.path.join(out_dir, "proc.npz"), out=out, err=err, n=n)
+        else:
+            assert res is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_band_processor_matches_single_processor(tmp_path):
+    """Image-level sharded run == the oracle's single-domain GridProcessor run (uint8 image, err, n)."""
+    mp.spawn(_proc_worker, args=(3, _free_port(), str(tmp_path)), nprocs=3, join=True)
+    from fpie_b200 import synth
+
+    src, mask, tgt = synth.make_problem("circle", 120, 90, seed=6)
+    big_tgt = np.random.default_rng(1).integers(0, 256, (150, 130, 3), dtype=np.uint8)
+    want = np_oracle.GridOracle("avg")
+    n = want.reset(src, mask, big_tgt, (0, 0), (20, 30))
+    want.step(10)
+    wout, werr = want.step(13)
+    z = np.load(tmp_path / "proc.npz")
+    assert int(z["n"]) == n
+    np.testing.assert_array_equal(z["out"], wout)
+    np.testing.assert_allclose(z["err"], werr, rtol=1e-5)
+
+
+def test_canonical_crop_matches_oracle():
+    from fpie_b200 import band, synth
+
+    for kind in ("circle", "star", "holes", "square"):
+        mask = synth.make_mask(kind, 61, 77, seed=2)
+        got_mask, box = band.canonical_crop(np.repeat(mask[:, :, None], 3, 2))
+        m_full, wbox = np_oracle.canonical_mask(mask)
+        assert box == wbox
+        np.testing.assert_array_equal(got_mask > 0, m_full[wbox[0] : wbox[1], wbox[2] : wbox[3]] > 0)
+    with pytest.raises(RuntimeError, match="empty"):
+        band.canonical_crop(np.zeros((9, 9), np.uint8))

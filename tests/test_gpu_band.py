@@ -98,6 +98,52 @@ def test_thread_bands_from_image_slabs(kind):
         np.testing.assert_allclose(err, c_oracle.grid_residual(mc, want, g)[1], rtol=1e-5)
 
 
+def test_thread_band_processor_image_level():
+    """BandGridProcessor: full images in on every rank, blended target out on rank 0."""
+    import torch
+
+    import fpie_b200
+    from fpie_b200 import band, synth
+
+    src, mask, tgt = synth.make_problem("star", 600, 500, seed=12)
+    big_tgt = np.random.default_rng(4).integers(0, 256, (700, 640, 3), dtype=np.uint8)
+    world = 3
+    dist = ThreadDist(world)
+    results, errors = [None] * world, []
+
+    def work(rank):
+        try:
+            dist.bind(rank)
+            torch.cuda.set_device(0)
+            proc = band.BandGridProcessor("max", band.CudaBandCore(fpie_b200.GridSolver(8, 8, device=0)), dist, halo=16)
+            n = proc.reset(src, mask, big_tgt, (0, 0), (40, 70))
+            proc.sync()
+            proc.step(20)
+            results[rank] = (n, proc.step(31))
+        except Exception as exc:
+            errors.append(exc)
+            try:
+                dist.bar.abort()
+            except Exception:
+                pass
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    want = np_oracle.GridOracle("max")
+    n = want.reset(src, mask, big_tgt, (0, 0), (40, 70))
+    want.t = c_oracle.grid_sweeps(want.mask, want.t, want.g, 51)
+    wout, werr = want.step(0)
+    assert results[0][0] == n and results[1][1] is None and results[2][1] is None
+    out, err = results[0][1]
+    np.testing.assert_array_equal(out, wout)
+    np.testing.assert_allclose(err, werr, rtol=1e-4)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
