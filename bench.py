@@ -261,7 +261,9 @@ def run_single(args, work, name):
     else:
         src, mask, tgt = synth.make_problem(work["mask"], size, size, seed=0)
         Proc = fpie_b200.GridProcessor if is_grid else fpie_b200.EquProcessor
-        kw = dict(block_k=args.block_k) if is_grid else {}
+        # EquSolver: the configs name the index-mapped gather path; "jacobi" would let the solver promote
+        # this (row-major, self-labelled) system to the tiled grid kernel -- reported separately below
+        kw = dict(block_k=args.block_k) if is_grid else dict(mode=args.equ_mode)
         proc = Proc(work["grad"], "b200", device=dev, **kw)
         reset_args = (src, mask, tgt, (0, 0), (0, 0))
     Proc = type(proc)
@@ -376,6 +378,7 @@ def run_single(args, work, name):
                    if unknowns * per_update > 2 * 126e6 else
                    "working set fits the 126 MB L2 (L2-resident configuration; reported separately from the HBM runs)"),
             "reset_s": reset_s,
+            "solver_path": core.info().get("path") if not is_grid else "tiled",
         },
         "roofline": roofline,
         "cpu_baseline": base,
@@ -540,6 +543,7 @@ def main():
     ap.add_argument("--halo", type=int, default=16, help="halo depth (rows) of the row-band sharding")
     ap.add_argument("--size", type=int, default=0, help="override the image side")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--equ-mode", default="gather", choices=["gather", "jacobi", "redblack"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     name = args.workload or ("cfg2" if args.gpus == 1 else "cfg4")

@@ -214,11 +214,12 @@ API int fpie_b200_equ_fetch(fpie_b200_equ *e, uint8_t *out_img, float *out_err3)
   NEED(e);
   return guarded([&] { e->impl.fetch(out_img, out_err3); });
 }
-API int fpie_b200_equ_info(fpie_b200_equ *e, int64_t *unknowns, int64_t *launches) {
+API int fpie_b200_equ_info(fpie_b200_equ *e, int64_t *unknowns, int64_t *launches, int *path) {
   NEED(e);
   return guarded([&] {
     if (unknowns) *unknowns = e->impl.stats().unknowns;
-    if (launches) *launches = e->impl.stats().launches;
+    if (launches) *launches = e->impl.launches();
+    if (path) *path = e->impl.path();
   });
 }
 API int fpie_b200_equ_reset_from_images(fpie_b200_equ *e, const uint8_t *src, int sh, int sw, const uint8_t *mask,

@@ -141,6 +141,29 @@ __global__ void compact_index_kernel(long long N, const int4 *__restrict__ A, in
   UD[i] = make_int2(a.x | (a.z != 0 ? (int)0x80000000 : 0), a.y | (a.w != 0 ? (int)0x80000000 : 0));
 }
 
+// Does A describe exactly the 4-neighbour structure of the mask that partition() labelled?
+// (row-major ids, absent neighbours = 0, no masked pixel on the frame)
+__global__ void check_grid_structure_kernel(int n, int m, const int32_t *__restrict__ mask,
+                                            const int32_t *__restrict__ ids, const int4 *__restrict__ A,
+                                            int *__restrict__ bad) {
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= (long long)n * m) return;
+  if (!(mask[p] > 0)) return;
+  const int r = (int)(p / m), c = (int)(p % m);
+  if (r == 0 || c == 0 || r == n - 1 || c == m - 1) {
+    atomicExch(bad, 1);
+    return;
+  }
+  const int4 a = A[ids[p]];
+  const long long q[4] = {p - m, p + m, p - 1, p + 1};
+  const int got[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int want = mask[q[k]] > 0 ? ids[q[k]] : 0;
+    if (got[k] != want) atomicExch(bad, 1);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // sweep / residual / output
 // ---------------------------------------------------------------------------
@@ -405,8 +428,11 @@ void EquSolver::label(const int32_t *dev_mask, int n, int m, int32_t *dev_ids) {
 }
 
 void EquSolver::set_mode(int mode) {
-  FPIE_REQUIRE(mode == 0 || mode == 1, "EquSolver mode must be 0 (Jacobi) or 1 (red-black Gauss-Seidel)");
-  mode_ = mode;
+  FPIE_REQUIRE(mode >= 0 && mode <= 2, "EquSolver mode must be 0 (Jacobi), 1 (red-black Gauss-Seidel) or 2 (Jacobi, gather only)");
+  mode_ = (mode == 1) ? 1 : 0;
+  no_promote_ = (mode == 2);
+  part_n_ = part_m_ = 0;
+  promoted_ = false;
   ready_ = false;
 }
 
@@ -415,12 +441,18 @@ void EquSolver::partition(int n, int m, const int32_t *mask, int64_t mask_rs, in
   FPIE_REQUIRE(mask_cs == 1 && mask_rs >= m, "partition: mask rows must be contiguous (column stride 1)");
   FPIE_REQUIRE((int64_t)n * m < (int64_t)1 << 31, "partition: more than 2^31 pixels");
   DeviceGuard guard(device_);
+  if (promoted_) {  // the promoted state indexes through ids_: bring it home before they are overwritten
+    pull_tiled_state();
+    promoted_ = false;
+  }
   const size_t count = (size_t)n * m;
   istage_.resize(count);
   ids_.resize(count);
   CUDA_CHECK(cudaMemcpy2DAsync(istage_.ptr, (size_t)m * 4, mask, (size_t)mask_rs * 4, (size_t)m * 4, n,
                                cudaMemcpyHostToDevice, stream_));
   label(istage_.ptr, n, m, ids_.ptr);
+  part_n_ = n;
+  part_m_ = m;
   CUDA_CHECK(cudaMemcpyAsync(out_ids, ids_.ptr, count * 4, cudaMemcpyDeviceToHost, stream_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));
 }
@@ -441,6 +473,7 @@ void EquSolver::reset(int64_t N, const int32_t *A, const float *X, const float *
   DeviceGuard guard(device_);
   ready_ = false;
   fused_ = false;
+  promoted_ = false;
   allocate(N);
   stage_.resize((size_t)N * 3);
   CUDA_CHECK(cudaMemcpyAsync(A_.ptr, A, (size_t)N * 16, cudaMemcpyHostToDevice, stream_));
@@ -457,7 +490,49 @@ void EquSolver::reset(int64_t N, const int32_t *A, const float *X, const float *
   FPIE_REQUIRE(*host_flag_ == 0, "EquSolver.reset: A holds an index outside [0, N)");
   stats_.unknowns = N - 1;
   compact_tables();
+  promoted_ = false;
+  bool zero_row = true;  // the grid embedding needs X[0] = B[0] = 0 and A[0] = 0 (the Processor's row 0)
+  for (int k = 0; k < 3; ++k) zero_row = zero_row && X[k] == 0.f && B[k] == 0.f;
+  for (int k = 0; k < 4; ++k) zero_row = zero_row && A[k] == 0;
+  if (structured_ && zero_row && part_n_ > 0) {
+    // does A match the mask this solver labelled in partition()?  (the reference flow: process.py:187, 270)
+    const long long px = (long long)part_n_ * part_m_;
+    int32_t last = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&last, ids_.ptr + (px - 1), 4, cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaMemsetAsync(flag_.ptr, 0, sizeof(int), stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    if ((int64_t)last == N - 1) {
+      check_grid_structure_kernel<<<blocks_for(px, 256), 256, 0, stream_>>>(part_n_, part_m_, istage_.ptr, ids_.ptr,
+                                                                            A_.ptr, flag_.ptr);
+      CUDA_CHECK(cudaGetLastError());
+      stats_.launches += 1;
+      CUDA_CHECK(cudaMemcpyAsync(host_flag_, flag_.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+      CUDA_CHECK(cudaStreamSynchronize(stream_));
+      if (*host_flag_ == 0) try_promote(part_n_, part_m_);
+    }
+  }
   ready_ = true;
+}
+
+// Promotion: an Equ system whose ids are the row-major labels of a known crop IS a grid problem --
+// state X on the masked pixels and 0 elsewhere, gradient B -- and
+//   ((((B + X[up]) + X[down]) + X[left]) + X[right]) / 4
+// is exactly what the grid kernel evaluates there (absent neighbours read the constant 0 in both
+// formulations), so the temporally blocked kernel produces the same bits several times faster.
+void EquSolver::try_promote(int n, int m) {
+  if (mode_ != 0 || no_promote_) return;
+  if (!tiled_) tiled_.reset(new GridSolver(device_, stream_, 0, 0));
+  EquEmbed e{n, m, istage_.ptr, ids_.ptr, X_[cur_].ptr, B_.ptr, pitch_};
+  tiled_->reset_from_equ(e);
+  promoted_ = true;
+  tiled_dirty_ = false;
+}
+
+void EquSolver::pull_tiled_state() {
+  if (!promoted_ || !tiled_dirty_) return;
+  EquEmbed e{part_n_, part_m_, istage_.ptr, ids_.ptr, X_[cur_].ptr, B_.ptr, pitch_};
+  tiled_->export_to_equ(e);
+  tiled_dirty_ = false;
 }
 
 void EquSolver::compact_tables() {
@@ -519,6 +594,10 @@ void EquSolver::reset_from_images(const uint8_t *src, int sh, int sw, const uint
   fused_ = true;
   stats_.unknowns = K;
   compact_tables();
+  part_n_ = b.n;
+  part_m_ = b.m;
+  promoted_ = false;
+  try_promote(b.n, b.m);
   ready_ = true;
   if (out_n) *out_n = K + 1;
   if (out_box4) {
@@ -547,6 +626,11 @@ void EquSolver::sweeps_async(int iters) {
     CUDA_CHECK(cudaGetLastError());
     return;
   }
+  if (promoted_) {
+    tiled_->sweeps_async(iters);
+    tiled_dirty_ = tiled_dirty_ || iters > 0;
+    return;
+  }
   for (int i = 0; i < iters; ++i) {
     if (structured_)
       equ_sweep_lr_kernel<<<blocks_for(N_, block_), block_, 0, stream_>>>(N_, pitch_, ud_.ptr, B_.ptr, X_[cur_].ptr,
@@ -563,6 +647,7 @@ void EquSolver::sweeps_async(int iters) {
 void EquSolver::finish_async() {
   require_ready();
   DeviceGuard guard(device_);
+  pull_tiled_state();
   CUDA_CHECK(cudaMemsetAsync(err_.ptr, 0, 3 * sizeof(double), stream_));
   equ_residual_kernel<<<blocks_for(N_, 256), 256, 0, stream_>>>(N_, pitch_, A_.ptr, B_.ptr, X_[cur_].ptr, err_.ptr);
   equ_to_u8_kernel<<<blocks_for(N_, 256), 256, 0, stream_>>>(N_, pitch_, X_[cur_].ptr, img_.ptr);
@@ -596,6 +681,7 @@ void EquSolver::step_paste(int iters, uint8_t *out_crop, float *out_err3, int64_
   FPIE_REQUIRE(fused_, "step_paste needs a solver reset with reset_from_images");
   DeviceGuard guard(device_);
   sweeps_async(iters);
+  pull_tiled_state();
   CUDA_CHECK(cudaMemsetAsync(err_.ptr, 0, 3 * sizeof(double), stream_));
   equ_residual_kernel<<<blocks_for(N_, 256), 256, 0, stream_>>>(N_, pitch_, A_.ptr, B_.ptr, X_[cur_].ptr, err_.ptr);
   const int64_t K = N_ - 1;
@@ -619,6 +705,7 @@ void EquSolver::state(float *out) {
   require_ready();
   FPIE_REQUIRE(out, "state: null output");
   DeviceGuard guard(device_);
+  pull_tiled_state();
   stage_.resize((size_t)N_ * 3);
   planes_to_rows3_kernel<<<blocks_for(N_, 256), 256, 0, stream_>>>(N_, pitch_, X_[cur_].ptr, stage_.ptr);
   CUDA_CHECK(cudaGetLastError());
@@ -630,6 +717,7 @@ void EquSolver::state(float *out) {
 void EquSolver::system(int32_t *out_A, float *out_X, float *out_B) {
   require_ready();
   DeviceGuard guard(device_);
+  pull_tiled_state();
   stage_.resize((size_t)N_ * 3);
   if (out_A) CUDA_CHECK(cudaMemcpyAsync(out_A, A_.ptr, (size_t)N_ * 16, cudaMemcpyDeviceToHost, stream_));
   if (out_X) {

@@ -1,7 +1,10 @@
 // EquSolver: index-mapped (gather) Jacobi on a compacted list of unknowns.
 #pragma once
 
+#include <memory>
+
 #include "common.cuh"
+#include "grid_solver.cuh"
 
 namespace fpie {
 
@@ -31,7 +34,10 @@ class EquSolver {
   void system(int32_t *out_A, float *out_X, float *out_B);
 
   const EquStats &stats() const { return stats_; }
+  int64_t launches() const { return stats_.launches + (tiled_ ? tiled_->stats().launches : 0); }
   bool structured() const { return structured_; }
+  // 0 = generic int4 gather, 1 = compact-table gather, 2 = promoted to the tiled grid kernel, 3 = red-black
+  int path() const { return mode_ == 1 ? 3 : (promoted_ ? 2 : (structured_ ? 1 : 0)); }
 
  private:
   void require_ready() const;
@@ -40,6 +46,8 @@ class EquSolver {
   void scan_ids(const int32_t *dev_mask, int64_t count, int32_t *dev_ids);
   void label(const int32_t *dev_mask, int n, int m, int32_t *dev_ids);
   void compact_tables();
+  void try_promote(int n, int m);
+  void pull_tiled_state();
 
   int device_;
   cudaStream_t stream_;
@@ -55,6 +63,10 @@ class EquSolver {
   DeviceBuffer<int2> ud_;      // compact table (up, down, left/right presence bits)
   bool structured_ = false;    // left/right are always i-1 / i+1 or absent
   bool force_generic_ = false;
+  // promotion to the temporally blocked grid kernel (row-major ids on a known crop)
+  std::unique_ptr<GridSolver> tiled_;
+  bool promoted_ = false, tiled_dirty_ = false, no_promote_ = false;
+  int part_n_ = 0, part_m_ = 0;  // geometry of the last partition() / fused reset (0 = unknown)
   DeviceBuffer<float> X_[2];
   DeviceBuffer<float> B_;
   DeviceBuffer<float> stage_;

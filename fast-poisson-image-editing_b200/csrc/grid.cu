@@ -579,6 +579,51 @@ grid_build_kernel(PlaneGeom g, BlendImages b, uint32_t *__restrict__ bits, float
   }
 }
 
+// EquSolver promotion (see equ.cu): embed a row-major Equ system into the grid.  Unknown i sits on
+// its pixel with state X[i] and quarter-gradient B[i]/4; every other pixel is 0, because the Equ
+// formulation folds the boundary values into B and gathers the constant row 0 for absent neighbours.
+__global__ void __launch_bounds__(256)
+grid_from_equ_kernel(PlaneGeom g, EquEmbed e, uint32_t *__restrict__ bits, float *__restrict__ x0,
+                     float *__restrict__ x1, float *__restrict__ hq, unsigned long long *__restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (warp >= (long long)g.n * g.wpitch) return;
+  const int r = (int)(warp / g.wpitch);
+  const int pcol = (int)(warp % g.wpitch) * 32 + lane;
+  const int c = pcol - g.padc;
+  const bool inside = c >= 0 && c < g.m;
+  const long long p = (long long)r * g.m + c;
+  const bool on = inside && e.mask[p] > 0;
+  const uint32_t word = __ballot_sync(0xffffffffu, on);
+  const long long prow = r + g.padr;
+  if (lane == 0) {
+    bits[prow * g.wpitch + (pcol >> 5)] = word;
+    if (word) atomicAdd(count, (unsigned long long)__popc(word));
+  }
+  if (!on) return;  // planes were zero-filled
+  const long long off = prow * g.pitch + pcol;
+  const long long id = e.ids[p];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const float t = e.X[ch * e.pitch + id];
+    x0[ch * g.plane + off] = t;
+    x1[ch * g.plane + off] = t;
+    hq[ch * g.plane + off] = 0.25f * e.B[ch * e.pitch + id];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+grid_to_equ_kernel(PlaneGeom g, EquEmbed e, const float *__restrict__ x) {
+  const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= (long long)g.n * g.m) return;
+  if (!(e.mask[p] > 0)) return;
+  const int r = (int)(p / g.m), c = (int)(p % g.m);
+  const long long off = (long long)(r + g.padr) * g.pitch + c + g.padc;
+  const long long id = e.ids[p];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) e.X[ch * e.pitch + id] = x[ch * g.plane + off];
+}
+
 // ---------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------
@@ -709,6 +754,38 @@ void GridSolver::reset_batch(const uint8_t *src, const uint8_t *mask, const uint
   batch_ = BatchMap{batch, ph, pw, bcols};
   batch_err_.resize((size_t)batch * 3);
   build_from_upload();
+}
+
+void GridSolver::reset_from_equ(const EquEmbed &e) {
+  DeviceGuard guard(device_);
+  ready_ = false;
+  batch_ = BatchMap{0, 0, 0, 0};
+  layout(e.n, e.m);
+  const PlaneGeom &g = geom_;
+  for (auto &buf : x_) buf.resize((size_t)g.plane * 3);
+  hq_.resize((size_t)g.plane * 3);
+  bits_.resize((size_t)g.rows * g.wpitch);
+  img_.resize((size_t)g.n * g.m * 3);
+  CUDA_CHECK(cudaMemsetAsync(x_[0].ptr, 0, x_[0].bytes(), stream_));
+  CUDA_CHECK(cudaMemsetAsync(x_[1].ptr, 0, x_[1].bytes(), stream_));
+  CUDA_CHECK(cudaMemsetAsync(hq_.ptr, 0, hq_.bytes(), stream_));
+  CUDA_CHECK(cudaMemsetAsync(bits_.ptr, 0, bits_.bytes(), stream_));
+  CUDA_CHECK(cudaMemsetAsync(err_.ptr, 0, err_.bytes(), stream_));
+  const long long warps = (long long)g.n * g.wpitch;
+  grid_from_equ_kernel<<<blocks_for(warps * 32, 256), 256, 0, stream_>>>(
+      g, e, bits_.ptr, x_[0].ptr, x_[1].ptr, hq_.ptr, reinterpret_cast<unsigned long long *>(err_.ptr + 3));
+  CUDA_CHECK(cudaGetLastError());
+  stats_.launches += 1;
+  after_state_loaded();
+}
+
+void GridSolver::export_to_equ(const EquEmbed &e) {
+  require_ready();
+  DeviceGuard guard(device_);
+  const long long px = (long long)geom_.n * geom_.m;
+  grid_to_equ_kernel<<<blocks_for(px, 256), 256, 0, stream_>>>(geom_, e, x_[cur_].ptr);
+  CUDA_CHECK(cudaGetLastError());
+  stats_.launches += 1;
 }
 
 void GridSolver::build_from_upload() {

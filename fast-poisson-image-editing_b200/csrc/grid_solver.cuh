@@ -27,6 +27,17 @@ struct TileShape {
   int tile_h() const { return rows_per_thread * warps; }
 };
 
+// An EquSolver system whose unknowns are the masked pixels of an n x m crop in row-major order,
+// handed over on the device: mask[p] > 0 marks unknowns, ids[p] their row, X / B are channel planes.
+struct EquEmbed {
+  int n, m;
+  const int32_t *mask;
+  const int32_t *ids;
+  float *X;        // [3][pitch]
+  const float *B;  // [3][pitch]
+  long long pitch;
+};
+
 struct GridStats {
   int64_t unknowns = 0;
   int64_t launches = 0;
@@ -46,6 +57,9 @@ class GridSolver {
                          int64_t *out_n, int32_t *out_box4, bool crop = true);
   void reset_batch(const uint8_t *src, const uint8_t *mask, const uint8_t *tgt, int batch, int ph, int pw, int mc,
                    int grad_mode);
+  // EquSolver promotion: state = X on masked pixels and 0 elsewhere, gradient = B (see equ.cu)
+  void reset_from_equ(const EquEmbed &e);
+  void export_to_equ(const EquEmbed &e);
   void sweeps_async(int iters);
   void finish_async();
   void sync();

@@ -54,7 +54,7 @@ SIGNATURES = {
     "fpie_b200_equ_finish_async": [c_void_p],
     "fpie_b200_equ_sync": [c_void_p],
     "fpie_b200_equ_fetch": [c_void_p, u8p, f32p],
-    "fpie_b200_equ_info": [c_void_p, i64p, i64p],
+    "fpie_b200_equ_info": [c_void_p, i64p, i64p, intp],
     "fpie_b200_equ_reset_from_images": [c_void_p, u8p, c_int, c_int, u8p, c_int, c_int, c_int, u8p, c_int, c_int,
                                         c_int, c_int, c_int, c_int, c_int, i64p, i32p],
     "fpie_b200_equ_step_paste": [c_void_p, c_int, u8p, f32p],

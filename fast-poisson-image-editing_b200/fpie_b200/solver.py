@@ -261,12 +261,17 @@ class GridSolver(_Handle):
 class EquSolver(_Handle):
     """Drop-in for ``core_cuda.EquSolver(block_size)`` (fpie/process.py:173-174)."""
 
-    MODES = {"jacobi": 0, "redblack": 1}
+    MODES = {"jacobi": 0, "redblack": 1, "gather": 2}
+    PATHS = {0: "gather-int4", 1: "gather-compact", 2: "tiled", 3: "redblack"}
 
     def __init__(self, block_size: int = 256, device: int | None = None, mode: str = "jacobi"):
-        """``mode="redblack"`` selects the reference OpenMP backend's red-black Gauss-Seidel
-        (fpie/core/openmp/equ.cc:22-56, 107-118) instead of true Jacobi; ``partition`` then labels
-        odd pixels before even ones, exactly as ``core_openmp.EquSolver.partition`` does."""
+        """``mode="jacobi"`` (default): true Jacobi; when the system is provably the 4-neighbour structure
+        of a mask this solver labelled (``partition`` / ``reset_from_images``) it runs on the temporally
+        blocked grid kernel (same bits, several times faster), otherwise on the gather kernels.
+        ``mode="gather"``: Jacobi on the index-mapped gather kernels only.
+        ``mode="redblack"``: the reference OpenMP backend's red-black Gauss-Seidel
+        (fpie/core/openmp/equ.cc:22-56, 107-118); ``partition`` then labels odd pixels before even
+        ones, exactly as ``core_openmp.EquSolver.partition`` does."""
         super().__init__()
         if mode not in self.MODES:
             raise ValueError(f"mode must be one of {sorted(self.MODES)}")
@@ -400,9 +405,10 @@ class EquSolver(_Handle):
         return img, err
 
     def info(self) -> dict:
-        unk, launches = ctypes.c_int64(), ctypes.c_int64()
-        _lib.check(self._lib.fpie_b200_equ_info(self.handle, ctypes.byref(unk), ctypes.byref(launches)))
-        return dict(unknowns=unk.value, launches=launches.value)
+        unk, launches, path = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int()
+        _lib.check(self._lib.fpie_b200_equ_info(self.handle, ctypes.byref(unk), ctypes.byref(launches),
+                                                ctypes.byref(path)))
+        return dict(unknowns=unk.value, launches=launches.value, path=self.PATHS[path.value])
 
     def _need_reset(self):
         if self.N <= 0:

@@ -163,6 +163,11 @@ int fpie_b200_equ_destroy(fpie_b200_equ *e);
  * ids of this solver's own partition (or of reset_from_images). */
 #define FPIE_B200_EQU_JACOBI 0
 #define FPIE_B200_EQU_REDBLACK 1
+/* Jacobi through the index-mapped gather kernels only.  In FPIE_B200_EQU_JACOBI the solver may
+ * instead run the temporally blocked grid kernel when it can prove that the system is the 4-neighbour
+ * structure of a mask it labelled itself (partition / reset_from_images): same bits, several times
+ * faster; FPIE_B200_EQU_GATHER switches that promotion off. */
+#define FPIE_B200_EQU_GATHER 2
 int fpie_b200_equ_set_mode(fpie_b200_equ *e, int mode);
 
 /* EquSolver::partition(mask) -> ids (equ.cu:36-54; np_solver.py:14-16):
@@ -188,7 +193,8 @@ int fpie_b200_equ_sweeps_async(fpie_b200_equ *e, int iters);
 int fpie_b200_equ_finish_async(fpie_b200_equ *e);
 int fpie_b200_equ_sync(fpie_b200_equ *e);
 int fpie_b200_equ_fetch(fpie_b200_equ *e, uint8_t *out_img, float *out_err3);
-int fpie_b200_equ_info(fpie_b200_equ *e, int64_t *unknowns, int64_t *launches);
+/* path: 0 = generic int4 gather, 1 = compact-table gather, 2 = promoted to the tiled grid kernel, 3 = red-black */
+int fpie_b200_equ_info(fpie_b200_equ *e, int64_t *unknowns, int64_t *launches, int *path);
 
 /* Fused Processor-level reset (EquProcessor.reset, fpie/process.py:192-271)
  * on the device: mask canonicalisation, partition scan, index compaction and

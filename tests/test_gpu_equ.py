@@ -210,9 +210,9 @@ def test_config3_full_size_ring():
     from fpie_b200 import synth
 
     src, mask, tgt = synth.make_problem("ring", 8192, 8192, seed=0)
-    proc = fpie_b200.EquProcessor("avg", "b200")
+    proc = fpie_b200.EquProcessor("avg", "b200", mode="gather")  # the index-mapped gather path named by config 3
     n = proc.reset(src, mask, tgt, (0, 0), (0, 0))
-    assert n > 35_000_000
+    assert n > 35_000_000 and proc.core.info()["path"] == "gather-compact"
     A, X, B = proc.core.system()
     # ids are row-major: left / right neighbours are i-1 / i+1 wherever they are masked
     assert ((A[1:, 2] == 0) | (A[1:, 2] == np.arange(1, n) - 1)).all()
@@ -308,3 +308,71 @@ def test_unstructured_ids_use_the_generic_table(golden):
     s.reset(n, A, X, B)
     s.step(21)
     np.testing.assert_array_equal(s.state(), want)
+
+
+@pytest.mark.parametrize("kind,mode", [("ring", "avg"), ("star", "max"), ("holes", "src")])
+def test_promotion_to_tiled_kernel_is_bit_exact(kind, mode):
+    """The reference call sequence (partition -> reset -> step, process.py:187, 270, 275): when A is the
+    4-neighbour structure of the mask this solver labelled, EquSolver runs the temporally blocked grid
+    kernel; mode="gather" keeps the index-mapped kernels.  Both must give the same bits as the oracle."""
+    import fpie_b200
+    from fpie_b200 import synth
+
+    src, mask, tgt = synth.make_problem(kind, 420, 380, seed=3)
+    m_full, (x0, x1, y0, y1) = np_oracle.canonical_mask(mask)
+    crop = m_full[x0:x1, y0:y1]
+    results = {}
+    for solver_mode, want_path in (("jacobi", "tiled"), ("gather", "gather-compact")):
+        s = fpie_b200.EquSolver(256, mode=solver_mode)
+        ids = s.partition(crop)
+        n, A, X, B, _ = np_oracle.equ_system(src, mask, tgt, (0, 0), (0, 0), mode, ids=ids)
+        s.reset(n, A, X, B)
+        assert s.info()["path"] == want_path
+        s.step(17)
+        img, err = s.step(26)
+        results[solver_mode] = (s.state(), img, err)
+    want = c_oracle.equ_sweeps(A, X, B, 43)
+    for state, img, err in results.values():
+        np.testing.assert_array_equal(state, want)
+        np.testing.assert_array_equal(img, c_oracle.clip_u8(want))
+        np.testing.assert_allclose(err, c_oracle.equ_residual(A, want, B)[1], rtol=ERR_RTOL)
+    np.testing.assert_array_equal(results["jacobi"][2], results["gather"][2])  # same residual kernel, same bits
+
+
+def test_promotion_is_refused_when_the_system_does_not_match_the_mask(golden):
+    import fpie_b200
+
+    c = golden_case(golden, "holes_full")
+    m_full, (x0, x1, y0, y1) = np_oracle.canonical_mask(c["mask"])
+    crop = m_full[x0:x1, y0:y1]
+    n, A, X, B, _ = np_oracle.equ_system(c["src"], c["mask"], c["tgt"], c["off_src"], c["off_tgt"], "max")
+    s = fpie_b200.EquSolver(256)
+    # (1) labelled a different mask with the same number of unknowns: transposed crop
+    s.partition(np.ascontiguousarray(crop.T))
+    s.reset(n, A, X, B)
+    assert s.info()["path"] != "tiled"
+    s.step(9)
+    np.testing.assert_array_equal(s.state(), np_oracle.equ_sweeps(A, X, B, 9))
+    # (2) right mask, but one neighbour link cut (still a legal system): must stay on the gather path
+    s.partition(crop)
+    A2 = A.copy()
+    row = np.flatnonzero(A2[:, 0] > 0)[5]
+    A2[row, 0] = 0
+    s.reset(n, A2, X, B)
+    assert s.info()["path"] != "tiled"
+    s.step(9)
+    np.testing.assert_array_equal(s.state(), np_oracle.equ_sweeps(A2, X, B, 9))
+    # (3) non-zero constant row: the grid embedding does not apply
+    X3 = X.copy()
+    X3[0] = 1.0
+    s.reset(n, A, X3, B)
+    assert s.info()["path"] != "tiled"
+    s.step(5)
+    np.testing.assert_array_equal(s.state(), np_oracle.equ_sweeps(A, X3, B, 5))
+    # (4) the matching system is promoted, and a later partition() on the same solver demotes it safely
+    s.reset(n, A, X, B)
+    assert s.info()["path"] == "tiled"
+    s.step(6)
+    s.partition(np.ascontiguousarray(crop[:, ::-1]))
+    s.step(3)
+    np.testing.assert_array_equal(s.state(), np_oracle.equ_sweeps(A, X, B, 9))
