@@ -13,6 +13,15 @@ for p in (ROOT, PKG_ROOT):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # a fresh checkout has no built artefacts (they are git-ignored): build the C-ABI library once
+    # (nvcc cross-compiles without a GPU); the C oracle builds itself on first use
+    try:
+        from fpie_b200 import _build
+
+        if not os.path.exists(_build.LIB_PATH):
+            _build.build()
+    except Exception as exc:  # the ABI tests will then fail loudly with the import error
+        print(f"[conftest] could not build libfpie_b200.so: {exc}")
 
 
 @pytest.fixture(scope="session")
