@@ -1,0 +1,79 @@
+"""Property-based parity (hypothesis): random shapes, masks, offsets, gradient modes and sweep counts
+through the Processor API, GPU vs the numpy oracle -- fp32 state bit-exact, uint8 image identical."""
+
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+from oracle import np_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@st.composite
+def blends(draw):
+    mh = draw(st.integers(3, 70))
+    mw = draw(st.integers(3, 90))
+    seed = draw(st.integers(0, 2**31 - 1))
+    rng = np.random.default_rng(seed)
+    density = draw(st.sampled_from([0.15, 0.5, 0.9, 1.0]))
+    mask = (rng.random((mh, mw)) < density).astype(np.uint8) * draw(st.sampled_from([128, 200, 255]))
+    if draw(st.booleans()):
+        mask = np.repeat(mask[:, :, None], 3, axis=2)
+    pad_s = [draw(st.integers(0, 6)) for _ in range(4)]
+    pad_t = [draw(st.integers(0, 6)) for _ in range(4)]
+    src = rng.integers(0, 256, (mh + pad_s[0] + pad_s[1], mw + pad_s[2] + pad_s[3], 3), dtype=np.uint8)
+    tgt = rng.integers(0, 256, (mh + pad_t[0] + pad_t[1], mw + pad_t[2] + pad_t[3], 3), dtype=np.uint8)
+    mode = draw(st.sampled_from(["max", "src", "avg"]))
+    steps = draw(st.lists(st.integers(0, 23), min_size=1, max_size=3))
+    return src, mask, tgt, (pad_s[0], pad_s[2]), (pad_t[0], pad_t[2]), mode, steps
+
+
+def _has_unknowns(mask):
+    try:
+        np_oracle.canonical_mask(mask)
+        return True
+    except ValueError:
+        return False
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+@given(blends(), st.sampled_from(["grid", "equ", "equ-gather", "equ-redblack"]))
+def test_processor_matches_oracle(blend, kind):
+    import fpie_b200
+
+    src, mask, tgt, off_s, off_t, mode, steps = blend
+    if kind == "grid":
+        proc, orc = fpie_b200.GridProcessor(mode, "b200"), np_oracle.GridOracle(mode)
+    elif kind == "equ-redblack":
+        proc, orc = fpie_b200.EquProcessor(mode, "b200", mode="redblack"), None
+    else:
+        proc = fpie_b200.EquProcessor(mode, "b200", mode="gather" if kind == "equ-gather" else "jacobi")
+        orc = np_oracle.EquOracle(mode)
+    if not _has_unknowns(mask):
+        with pytest.raises(RuntimeError, match="empty"):
+            proc.reset(src, mask, tgt, off_s, off_t)
+        return
+    n = proc.reset(src, mask, tgt, off_s, off_t)
+    if orc is None:  # red-black: oracle system with the odd/even labelling
+        m_full, (x0, x1, y0, y1) = np_oracle.canonical_mask(mask)
+        ids, n_mid = np_oracle.partition_redblack(m_full[x0:x1, y0:y1])
+        N, A, X, B, index = np_oracle.equ_system(src, mask, tgt, off_s, off_t, mode, ids=ids)
+        assert n == N
+        canvas = tgt.copy()
+        for it in steps:
+            out, err = proc.step(it)
+            X = np_oracle.equ_sweeps_redblack(A, X, B, it, n_mid)
+            np.testing.assert_array_equal(proc.core.state(), X)
+            canvas[index] = np_oracle.clip_u8(X)[1:]
+            np.testing.assert_array_equal(out, canvas)
+        return
+    assert n == orc.reset(src, mask, tgt, off_s, off_t)
+    for it in steps:
+        out, err = proc.step(it)
+        wout, werr = orc.step(it)
+        state = proc.core.state()
+        np.testing.assert_array_equal(state, orc.t if kind == "grid" else orc.X)
+        np.testing.assert_array_equal(out, wout)
+        np.testing.assert_allclose(err, werr, rtol=1e-4, atol=1e-3)
