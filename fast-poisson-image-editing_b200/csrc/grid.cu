@@ -433,6 +433,10 @@ grid_sweepk_pipe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
   }
 }
 
+}  // namespace fpie
+#include "grid_pair.cuh"
+namespace fpie {
+
 // Classify the tile grid: flag bit0 = some masked pixel in the stored (inner)
 // region, bit1 = every pixel of the whole tile masked.  One CTA per tile.
 __global__ void classify_tiles_kernel(PlaneGeom g, const uint32_t *__restrict__ bits, int tiles_x, int tile_h,
@@ -917,6 +921,30 @@ void launch_pipe(const SweepArgs &a) {
     launch_pipe_h<R, NW, OCC, false>(a);
 }
 
+template <int R, int NW, bool H16>
+void launch_pair_h(const SweepArgs &a) {
+  auto kernel = grid_sweepk_pair_kernel<R, NW, H16>;
+  constexpr size_t smem = PairSmem<R, NW, H16>::TOTAL;
+  static int configured_device = -1;
+  int dev = 0;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  if (configured_device != dev) {
+    CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured_device = dev;
+  }
+  const int grid = std::min(a.ntiles, a.grid);
+  kernel<<<grid, NW * 32, smem, a.stream>>>(*a.tm_x, *a.tm_h, *a.tm_m, a.g, a.xout, a.tiles, a.ntiles, a.nsweeps,
+                                            a.halo_y, a.halo_x);
+}
+
+template <int R, int NW>
+void launch_pair(const SweepArgs &a) {
+  if (a.h16)
+    launch_pair_h<R, NW, true>(a);
+  else
+    launch_pair_h<R, NW, false>(a);
+}
+
 struct VariantInfo {
   int rows, warps, occ;
   bool pipe;
@@ -943,6 +971,10 @@ VariantInfo variant_info(int v) {
     case 14: return {7, 12, 2, true};
     case 15: return {6, 24, 1, true};
     case 16: return {6, 28, 1, true};
+    // packed-pair (FFMA2) kernels: rows = 2 x pair-rows per thread
+    case 20: return {14, 12, 1, true};
+    case 21: return {16, 12, 1, true};
+    case 22: return {12, 12, 1, true};
     default: throw Error("fpie_b200: unknown grid kernel variant");
   }
 }
@@ -1016,6 +1048,9 @@ void GridSolver::sweeps_async(int iters) {
       case 14: launch_pipe<7, 12, 2>(a); break;
       case 15: launch_pipe<6, 24, 1>(a); break;
       case 16: launch_pipe<6, 28, 1>(a); break;
+      case 20: launch_pair<7, 12>(a); break;
+      case 21: launch_pair<8, 12>(a); break;
+      case 22: launch_pair<6, 12>(a); break;
       default: throw Error("fpie_b200: unknown grid kernel variant");
     }
     cur_ ^= 1;

@@ -17,7 +17,7 @@ STATE_TOL = 1e-3
 ERR_RTOL = 1e-4
 
 VARIANTS = [(100, 0), (105, 5), (0, 0), (0, 1), (0, 3), (0, 16), (1, 0), (2, 8), (3, 3), (4, 2), (5, 6), (6, 7), (7, 5), (8, 4), (9, 12),
-            (10, 9), (11, 8), (12, 2)]  # (variant, block_k)
+            (10, 9), (11, 8), (12, 2), (20, 8), (20, 3), (21, 6), (22, 5), (120, 7)]  # (variant, block_k)
 
 
 def _solver(variant=0, block_k=0):
@@ -94,7 +94,7 @@ def test_processor_matches_reference_golden(golden, name, mode):
 
 
 @pytest.mark.parametrize("variant,block_k", [(0, 0), (0, 5), (1, 0), (2, 16), (3, 3), (4, 8), (5, 12), (6, 4), (7, 16), (8, 8), (9, 3), (10, 10),
-                                             (11, 1), (12, 7)])
+                                             (11, 1), (12, 7), (20, 0), (20, 13), (21, 4), (22, 16), (120, 8)])
 @pytest.mark.parametrize("shape,iters", [((3, 3), 4), ((4, 7), 9), ((61, 130), 37), ((257, 300), 50), ((300, 517), 23),
                                          ((700, 401), 40)])
 def test_random_grids_bitexact_vs_c_oracle(shape, iters, variant, block_k):
@@ -110,7 +110,7 @@ def test_random_grids_bitexact_vs_c_oracle(shape, iters, variant, block_k):
     assert s.info()["unknowns"] == int(mask.sum())
 
 
-@pytest.mark.parametrize("variant", [0, 100, 107, 4, 1])
+@pytest.mark.parametrize("variant", [0, 100, 107, 4, 1, 20, 120])
 def test_arbitrary_float_gradients(variant):
     """Core-level grads need not be multiples of 1/2 (the Processor's are): values
     that do not survive fp16 must take the fp32 streaming path and stay bit-exact;
@@ -281,7 +281,7 @@ def test_full_size_temporal_blocking_invariance():
 
     src, mask, tgt = synth.make_problem("circle", 4096, 4096, seed=0)
     ref = None
-    for variant, k in ((1, 0), (0, 8), (0, 16), (2, 4), (4, 8), (5, 12), (6, 5), (8, 8), (10, 6)):
+    for variant, k in ((1, 0), (0, 8), (0, 16), (2, 4), (4, 8), (5, 12), (6, 5), (8, 8), (10, 6), (20, 8), (20, 12), (22, 6)):
         proc = fpie_b200.GridProcessor("max", "b200")
         proc.core.close()
         proc.core = fpie_b200.GridSolver(8, 8, block_k=k, variant=variant)
