@@ -48,15 +48,9 @@ class BaseProcessor:
         """Run the device-side reset while a worker thread makes the Processor's private copy of
         the target (process.py:268 / 384); both release the GIL, so they overlap."""
         box = {}
-        old = self.tgt
 
         def copy():
-            # reuse the previous canvas when the target has the same shape (no fresh pages to fault in)
-            if old is not None and old.shape == tgt.shape and old.dtype == np.uint8 and not np.shares_memory(old, tgt):
-                np.copyto(old, tgt, casting="unsafe")
-                box["tgt"] = old
-            else:
-                box["tgt"] = np.array(tgt, dtype=np.uint8, copy=True)
+            box["tgt"] = np.array(tgt, dtype=np.uint8, copy=True)
 
         worker = threading.Thread(target=copy)
         worker.start()
