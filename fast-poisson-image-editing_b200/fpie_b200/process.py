@@ -47,18 +47,23 @@ class BaseProcessor:
     def _reset_with_canvas(self, tgt, device_reset):
         """Run the device-side reset while a worker thread makes the Processor's private copy of
         the target (process.py:268 / 384); both release the GIL, so they overlap."""
-        box = {}
+        canvas = np.empty(tgt.shape, np.uint8)
+        rows = tgt.shape[0]
+        parts = 4 if tgt.size >= (8 << 20) else 1  # large images: fault the fresh pages in from several threads
+        bounds = [rows * i // parts for i in range(parts + 1)]
 
-        def copy():
-            box["tgt"] = np.array(tgt, dtype=np.uint8, copy=True)
+        def copy(lo, hi):
+            np.copyto(canvas[lo:hi], tgt[lo:hi], casting="unsafe")
 
-        worker = threading.Thread(target=copy)
-        worker.start()
+        workers = [threading.Thread(target=copy, args=(bounds[i], bounds[i + 1])) for i in range(parts)]
+        for wk in workers:
+            wk.start()
         try:
             result = device_reset()
         finally:
-            worker.join()
-        self.tgt = box["tgt"]
+            for wk in workers:
+                wk.join()
+        self.tgt = canvas
         return result
 
     @staticmethod
