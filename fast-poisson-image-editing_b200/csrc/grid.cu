@@ -19,7 +19,14 @@
 #include "prep.cuh"
 #include "tma.cuh"
 
+#ifndef FPIE_SWEEP_UNROLL
+#define FPIE_SWEEP_UNROLL 2
+#endif
+
 namespace fpie {
+
+// copies of the sweep body in the tile loop: with two, the register rotation at the loop edge disappears
+constexpr int kSweepUnroll = FPIE_SWEEP_UNROLL;
 
 // ---------------------------------------------------------------------------
 // layout conversion
@@ -301,6 +308,10 @@ __device__ __forceinline__ void tile_sweep_split(float4 (&x)[R], const float4 (&
   row_update<MIXED>(x[R - 1], h[R - 1], prev, dn, mb[(R - 1) / 8] >> (((R - 1) % 8) * 4));
 }
 
+#ifndef FPIE_SWEEP_UNROLL
+#define FPIE_SWEEP_UNROLL 2  // two copies of the sweep body: the register rotation at the loop edge disappears
+#endif
+
 // Shared-memory layout of the pipelined kernel (all sections 128-byte aligned).
 template <int R, int NW, bool H16>
 struct PipeSmem {
@@ -405,7 +416,7 @@ grid_sweepk_pipe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     __syncthreads();  // every thread has drained the staging buffers
     if (threadIdx.x == 0 && t + stride < ntiles) issue(nxt);
 
-#pragma unroll 2
+#pragma unroll kSweepUnroll
     for (int s = 0; s < nsweeps; ++s) {
       if (td.full)
         tile_sweep_split<R, NW, false>(x, h, mb, mailbox, &bars[1], parity, mphase);
