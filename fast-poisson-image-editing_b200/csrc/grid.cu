@@ -20,12 +20,12 @@
 #include "tma.cuh"
 
 #ifndef FPIE_SWEEP_UNROLL
-#define FPIE_SWEEP_UNROLL 2
+#define FPIE_SWEEP_UNROLL 4
 #endif
 
 namespace fpie {
 
-// copies of the sweep body in the tile loop: with two, the register rotation at the loop edge disappears
+// copies of the sweep body in the tile loop: the register rotation at the loop edge is paid once per four sweeps
 constexpr int kSweepUnroll = FPIE_SWEEP_UNROLL;
 
 // ---------------------------------------------------------------------------
@@ -309,7 +309,7 @@ __device__ __forceinline__ void tile_sweep_split(float4 (&x)[R], const float4 (&
 }
 
 #ifndef FPIE_SWEEP_UNROLL
-#define FPIE_SWEEP_UNROLL 2  // two copies of the sweep body: the register rotation at the loop edge disappears
+#define FPIE_SWEEP_UNROLL 4  // two copies of the sweep body: the register rotation at the loop edge disappears
 #endif
 
 // Shared-memory layout of the pipelined kernel (all sections 128-byte aligned).
