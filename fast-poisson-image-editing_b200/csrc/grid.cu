@@ -308,10 +308,6 @@ __device__ __forceinline__ void tile_sweep_split(float4 (&x)[R], const float4 (&
   row_update<MIXED>(x[R - 1], h[R - 1], prev, dn, mb[(R - 1) / 8] >> (((R - 1) % 8) * 4));
 }
 
-#ifndef FPIE_SWEEP_UNROLL
-#define FPIE_SWEEP_UNROLL 4  // two copies of the sweep body: the register rotation at the loop edge disappears
-#endif
-
 // Shared-memory layout of the pipelined kernel (all sections 128-byte aligned).
 template <int R, int NW, bool H16>
 struct PipeSmem {
