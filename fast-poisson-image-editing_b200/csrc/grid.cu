@@ -654,12 +654,11 @@ GridSolver::GridSolver(int device, cudaStream_t stream, int block_k, int variant
     force_h32_ = true;
     variant_ -= 100;
   }
+  // variant 0 with block_k 0 = automatic: tile shape and blocking depth follow the grid size at reset
+  auto_tune_ = (variant_ == 0 && block_k <= 0);
   if (block_k <= 0) block_k = 8;
   FPIE_REQUIRE(block_k <= MAX_BLOCK_K, "block_k must be in 1..16");
-  block_k_ = block_k;
-  halo_x_ = (int)round_up(block_k_, 4);
-  shape_ = shape_for(variant_);
-  FPIE_REQUIRE(shape_.tile_h() > 2 * block_k_, "block_k too deep for the tile height");
+  configure(variant_, block_k);
   err_.resize(4);
   CUDA_CHECK(cudaMallocHost(&host_err_, 4 * sizeof(double)));
 }
@@ -669,10 +668,34 @@ GridSolver::~GridSolver() {
   if (host_err_) cudaFreeHost(host_err_);
 }
 
+void GridSolver::configure(int variant, int block_k) {
+  variant_ = variant;
+  block_k_ = block_k;
+  halo_x_ = (int)round_up(block_k_, 4);
+  shape_ = shape_for(variant_);
+  FPIE_REQUIRE(shape_.tile_h() > 2 * block_k_, "block_k too deep for the tile height");
+}
+
+// Automatic configuration (measured on B200, tools/tune_grid.py): small grids cannot fill 148 SMs with
+// 168-row tiles and pay the per-launch latency once per pass, so they get 64-row tiles on two CTAs per
+// SM and deeper temporal blocking; large grids get the tall tile with k = 8.
+void GridSolver::auto_configure(int n, int m) {
+  const long long px = (long long)n * m;
+  if (px <= 450000)
+    configure(12, 16);
+  else if (px <= 1600000)
+    configure(12, 8);
+  else if (px <= 6000000)
+    configure(11, 8);
+  else
+    configure(0, 8);
+}
+
 void GridSolver::require_ready() const { FPIE_REQUIRE(ready_, "GridSolver: step/state called before reset"); }
 
 void GridSolver::layout(int n, int m) {
   FPIE_REQUIRE(n >= 1 && m >= 1, "GridSolver.reset: empty grid");
+  if (auto_tune_) auto_configure(n, m);
   const int step_x = TILE_W - 2 * halo_x_, step_y = shape_.tile_h() - 2 * block_k_;
   const int tiles_x = (int)ceil_div(m, step_x), tiles_y = (int)ceil_div(n, step_y);
   PlaneGeom g{};

@@ -81,6 +81,8 @@ class GridSolver {
   void build_tiles();
   void after_state_loaded();
   void make_tensor_maps();
+  void configure(int variant, int block_k);
+  void auto_configure(int n, int m);
   void build_from_upload();
   static TileShape shape_for(int variant);
 
@@ -89,6 +91,7 @@ class GridSolver {
   int block_k_;
   int halo_x_;
   int variant_;
+  bool auto_tune_ = false;
   int sm_count_ = 0;
   TileShape shape_{16, 12};
 
