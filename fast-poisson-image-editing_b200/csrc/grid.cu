@@ -368,8 +368,12 @@ grid_sweepk_pipe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
   int t = blockIdx.x;
   if (t >= ntiles) return;
   const int stride = gridDim.x;
-  int2 cur = tiles[t];
+  int2 cur = tiles[t];  // (the tile list is not written by the sweep kernels: safe before the dependency wait)
   int2 nxt = (t + stride < ntiles) ? tiles[t + stride] : cur;
+  // programmatic dependent launch: let the next pass get scheduled, then wait for the previous pass --
+  // it wrote the state this pass reads and read the buffer this pass overwrites
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (threadIdx.x == 0) issue(cur);
   int parity = 0;
   uint32_t phase = 0, mphase = 0;
@@ -939,8 +943,22 @@ void launch_pipe_h(const SweepArgs &a) {
     configured_device = dev;
   }
   const int grid = std::min(a.ntiles, a.grid * OCC);
-  kernel<<<grid, NW * 32, smem, a.stream>>>(*a.tm_x, *a.tm_h, *a.tm_m, a.g, a.xout, a.tiles, a.ntiles, a.nsweeps,
-                                            a.halo_y, a.halo_x);
+  // programmatic dependent launch: the next pass may be scheduled while this one drains; its CTAs run
+  // their prologue (barrier init, descriptor fetch) and block in griddepcontrol.wait until this grid
+  // has completed, so the per-launch latency overlaps the tail instead of following it
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NW * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = a.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  // (measured: a win once there is at least one tile per SM, a loss for grids of a few dozen tiles)
+  cfg.numAttrs = (a.ntiles >= a.grid) ? 1 : 0;
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, *a.tm_x, *a.tm_h, *a.tm_m, a.g, a.xout, a.tiles, a.ntiles, a.nsweeps,
+                                a.halo_y, a.halo_x));
 }
 
 template <int R, int NW, int OCC>
