@@ -1,5 +1,6 @@
 // Shared helpers for the fpie_b200 CUDA sources (sm_100a only).
 #pragma once
+#include <algorithm>
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,11 +28,14 @@ inline void cuda_check(cudaError_t e, const char *what, const char *file, int li
     if (!(cond)) throw ::fpie::Error(msg); \
   } while (0)
 
-// RAII device buffer (cudaMalloc / cudaFree on a fixed device).
+// RAII device buffer (cudaMalloc / cudaFree on a fixed device).  resize() keeps an allocation that is
+// large enough and not wastefully so: repeated reset() calls (the GUI, batch services) then do no
+// cudaMalloc / cudaFree at all -- both synchronise the device and cost milliseconds.
 template <typename T>
 struct DeviceBuffer {
   T *ptr = nullptr;
-  size_t count = 0;
+  size_t count = 0;     // logical element count
+  size_t capacity = 0;  // allocated element count
   DeviceBuffer() = default;
   DeviceBuffer(const DeviceBuffer &) = delete;
   DeviceBuffer &operator=(const DeviceBuffer &) = delete;
@@ -39,14 +43,18 @@ struct DeviceBuffer {
   void release() {
     if (ptr) cudaFree(ptr);
     ptr = nullptr;
-    count = 0;
+    count = capacity = 0;
   }
   void resize(size_t n) {
-    if (n == count && ptr) return;
+    const size_t keep_bytes = std::max<size_t>(2 * n * sizeof(T), (size_t)32 << 20);
+    if (ptr && n && n <= capacity && capacity * sizeof(T) <= keep_bytes) {
+      count = n;
+      return;
+    }
     release();
     if (n) {
       CUDA_CHECK(cudaMalloc(&ptr, n * sizeof(T)));
-      count = n;
+      count = capacity = n;
     }
   }
   size_t bytes() const { return count * sizeof(T); }

@@ -553,7 +553,7 @@ void EquSolver::reset_from_images(const uint8_t *src, int sh, int sw, const uint
                                   int64_t *out_n, int32_t *out_box4) {
   DeviceGuard guard(device_);
   ready_ = false;
-  BlendUpload up;
+  BlendUpload &up = upload_;  // device copies of the images are kept between resets (no malloc / free per call)
   up.upload(stream_, src, sh, sw, mask, mh, mw, mc, tgt, th, tw, h0, w0, h1, w1, grad_mode);
   const BlendImages &b = up.images();
   const long long count = (long long)b.n * b.m;

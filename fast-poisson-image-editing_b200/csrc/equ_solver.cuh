@@ -71,6 +71,7 @@ class EquSolver {
   DeviceBuffer<float> B_;
   DeviceBuffer<float> stage_;
   DeviceBuffer<int32_t> istage_;
+  BlendUpload upload_;
   DeviceBuffer<int32_t> ids_;
   DeviceBuffer<uint32_t> block_sums_;
   DeviceBuffer<uint8_t> img_;

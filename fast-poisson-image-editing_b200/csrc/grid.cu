@@ -27,6 +27,10 @@ namespace fpie {
 
 // copies of the sweep body in the tile loop: the register rotation at the loop edge is paid once per four sweeps
 constexpr int kSweepUnroll = FPIE_SWEEP_UNROLL;
+#ifndef FPIE_PULL_AHEAD
+#define FPIE_PULL_AHEAD 4
+#endif
+constexpr int kPullAhead = FPIE_PULL_AHEAD;  // rows before the strip's end at which the neighbours' edge rows are pulled
 
 // ---------------------------------------------------------------------------
 // layout conversion
@@ -291,7 +295,7 @@ __device__ __forceinline__ void tile_sweep_split(float4 (&x)[R], const float4 (&
   float4 up, dn;
   // the neighbours' rows are pulled a few interior rows before they are needed, so that the
   // barrier check and the shared-memory latency hide behind the remaining interior rows
-  constexpr int PULL_ROW = (R >= 8) ? R - 4 : R - 2;
+  constexpr int PULL_ROW = (R >= 18) ? R - 8 : (R >= 8) ? R - kPullAhead : R - 2;
 #pragma unroll
   for (int i = 1; i < R - 1; ++i) {
     if (i == PULL_ROW) {
@@ -416,7 +420,10 @@ grid_sweepk_pipe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     __syncthreads();  // every thread has drained the staging buffers
     if (threadIdx.x == 0 && t + stride < ntiles) issue(nxt);
 
-#pragma unroll kSweepUnroll
+    // (tall register tiles: the body is long enough that unrolling past 2 only costs instruction cache --
+    // measured 853 -> 877 Gupd/s on cfg2 for R = 21; 2 is the minimum that keeps `parity` static)
+    constexpr int UNROLL = (R >= 18) ? 2 : kSweepUnroll;
+#pragma unroll UNROLL
     for (int s = 0; s < nsweeps; ++s) {
       if (td.full)
         tile_sweep_split<R, NW, false>(x, h, mb, mailbox, &bars[1], parity, mphase);
@@ -658,11 +665,13 @@ GridSolver::GridSolver(int device, cudaStream_t stream, int block_k, int variant
     force_h32_ = true;
     variant_ -= 100;
   }
-  // variant 0 with block_k 0 = automatic: tile shape and blocking depth follow the grid size at reset
-  auto_tune_ = (variant_ == 0 && block_k <= 0);
+  // variant 0 = automatic tile shape, block_k 0 = automatic blocking depth: both follow the grid size at
+  // reset (variant 39 is the fixed 14 x 12 shape that variant 0 used to name)
+  auto_tune_ = (variant_ == 0);
+  auto_k_ = (block_k <= 0);
   if (block_k <= 0) block_k = 8;
   FPIE_REQUIRE(block_k <= MAX_BLOCK_K, "block_k must be in 1..16");
-  configure(variant_, block_k);
+  configure(variant_ == 0 ? 39 : variant_, block_k);
   err_.resize(4);
   CUDA_CHECK(cudaMallocHost(&host_err_, 4 * sizeof(double)));
 }
@@ -680,19 +689,24 @@ void GridSolver::configure(int variant, int block_k) {
   FPIE_REQUIRE(shape_.tile_h() > 2 * block_k_, "block_k too deep for the tile height");
 }
 
-// Automatic configuration (measured on B200, tools/tune_grid.py): small grids cannot fill 148 SMs with
-// 168-row tiles and pay the per-launch latency once per pass, so they get 64-row tiles on two CTAs per
-// SM and deeper temporal blocking; large grids get the tall tile with k = 8.
+// Automatic configuration (measured on B200, tools/tune_grid.py, profiles/r01_tune_variants_k.json): small
+// grids cannot fill 148 SMs with 168-row tiles and pay the per-launch latency once per pass, so they get
+// 64-row tiles on two CTAs per SM and deeper temporal blocking; mid-size grids 84-row tiles (21 rows per
+// thread, four warps, two CTAs per SM); large grids the 168-row tile as 8 warps x 21 rows with k = 8.
 void GridSolver::auto_configure(int n, int m) {
   const long long px = (long long)n * m;
+  int v, k;
   if (px <= 450000)
-    configure(12, 16);
+    v = 12, k = 16;
   else if (px <= 1600000)
-    configure(12, 8);
+    v = 12, k = 8;
   else if (px <= 6000000)
-    configure(11, 8);
+    v = 36, k = 8;
   else
-    configure(0, 8);
+    v = 24, k = 8;
+  if (!auto_k_) k = block_k_;  // the caller's depth wins; take the tallest tile if the small one cannot hold it
+  if (shape_for(v).tile_h() <= 2 * k) v = 24;
+  configure(v, k);
 }
 
 void GridSolver::require_ready() const { FPIE_REQUIRE(ready_, "GridSolver: step/state called before reset"); }
@@ -1002,7 +1016,8 @@ struct VariantInfo {
 // rows/thread x warps, CTAs per SM; "pipe" = TMA-staged + split-phase exchange.
 VariantInfo variant_info(int v) {
   switch (v) {
-    case 0: return {14, 12, 1, true};  // default
+    case 0:  // (automatic: replaced by a concrete shape at reset)
+    case 39: return {14, 12, 1, true};
     case 1: return {16, 12, 1, false};  // (tile shape unused: one sweep per launch)
     case 2: return {16, 8, 1, false};
     case 3: return {8, 16, 1, false};
@@ -1019,6 +1034,22 @@ VariantInfo variant_info(int v) {
     case 14: return {7, 12, 2, true};
     case 15: return {6, 24, 1, true};
     case 16: return {6, 28, 1, true};
+    case 17: return {15, 12, 1, true};
+    // two warps per scheduler: each sub-partition's 16384 registers then allow up to 255 per thread
+    case 18: return {20, 8, 1, true};
+    case 19: return {22, 8, 1, true};
+    case 23: return {24, 8, 1, true};
+    case 24: return {21, 8, 1, true};
+    case 25: return {19, 8, 1, true};
+    case 26: return {18, 8, 1, true};
+    case 27: return {24, 7, 1, true};
+    case 28: return {28, 6, 1, true};
+    // four warps per CTA, several CTAs per SM: small tiles for small grids without giving up rows per thread
+    case 29: return {16, 4, 2, true};
+    case 35: return {16, 4, 3, true};
+    case 36: return {21, 4, 2, true};
+    case 37: return {12, 4, 3, true};
+    case 38: return {8, 4, 4, true};
     // packed-pair (FFMA2) kernels: rows = 2 x pair-rows per thread
     case 20: return {14, 12, 1, true};
     case 21: return {16, 12, 1, true};
@@ -1080,7 +1111,7 @@ void GridSolver::sweeps_async(int iters) {
     a.xout = x_[cur_ ^ 1].ptr;
     a.tm_x = &tm_x_[cur_];
     switch (variant_) {
-      case 0: launch_pipe<14, 12, 1>(a); break;
+      case 39: launch_pipe<14, 12, 1>(a); break;
       case 2: launch_direct<16, 8>(a); break;
       case 3: launch_direct<8, 16>(a); break;
       case 4: launch_direct<16, 12>(a); break;
@@ -1096,6 +1127,20 @@ void GridSolver::sweeps_async(int iters) {
       case 14: launch_pipe<7, 12, 2>(a); break;
       case 15: launch_pipe<6, 24, 1>(a); break;
       case 16: launch_pipe<6, 28, 1>(a); break;
+      case 17: launch_pipe<15, 12, 1>(a); break;
+      case 18: launch_pipe<20, 8, 1>(a); break;
+      case 19: launch_pipe<22, 8, 1>(a); break;
+      case 23: launch_pipe<24, 8, 1>(a); break;
+      case 24: launch_pipe<21, 8, 1>(a); break;
+      case 25: launch_pipe<19, 8, 1>(a); break;
+      case 26: launch_pipe<18, 8, 1>(a); break;
+      case 27: launch_pipe<24, 7, 1>(a); break;
+      case 28: launch_pipe<28, 6, 1>(a); break;
+      case 29: launch_pipe<16, 4, 2>(a); break;
+      case 35: launch_pipe<16, 4, 3>(a); break;
+      case 36: launch_pipe<21, 4, 2>(a); break;
+      case 37: launch_pipe<12, 4, 3>(a); break;
+      case 38: launch_pipe<8, 4, 4>(a); break;
       case 20: launch_pair<7, 12>(a); break;
       case 21: launch_pair<8, 12>(a); break;
       case 22: launch_pair<6, 12>(a); break;

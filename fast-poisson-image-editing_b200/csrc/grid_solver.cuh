@@ -91,7 +91,8 @@ class GridSolver {
   int block_k_;
   int halo_x_;
   int variant_;
-  bool auto_tune_ = false;
+  bool auto_tune_ = false;  // tile shape chosen at reset
+  bool auto_k_ = false;     // blocking depth chosen at reset
   int sm_count_ = 0;
   TileShape shape_{16, 12};
 

@@ -61,8 +61,10 @@ int fpie_b200_device_info(int device, char *name, int name_len, int *sm_count, i
 
 /* GridSolver(grid_x, grid_y) constructor (fpie/process.py:312-313).
  * `block_k` = Jacobi sweeps fused per pass over HBM (temporal blocking depth,
- * 1..16; 0 = default); `variant` selects a kernel family for testing
- * (0 = default, 1 = one-sweep-per-launch kernels only). */
+ * 1..16; 0 = chosen from the grid size at reset); `variant` selects a kernel
+ * family / register-tile shape for testing and tuning (0 = chosen from the
+ * grid size at reset, 1 = one-sweep-per-launch kernels only; the table is in
+ * csrc/grid.cu, variant_info). */
 int fpie_b200_grid_create(int device, void *stream, int block_k, int variant, fpie_b200_grid **out);
 int fpie_b200_grid_destroy(fpie_b200_grid *g);
 
