@@ -543,7 +543,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--iters", type=int, default=0, help="override sweeps per step")
     ap.add_argument("--block-k", type=int, default=0)
-    ap.add_argument("--halo", type=int, default=16, help="halo depth (rows) of the row-band sharding")
+    ap.add_argument("--halo", type=int, default=24, help="halo depth (rows) of the row-band sharding")
     ap.add_argument("--size", type=int, default=0, help="override the image side")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--equ-mode", default="gather", choices=["gather", "jacobi", "redblack"])

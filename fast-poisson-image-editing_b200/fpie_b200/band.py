@@ -97,9 +97,12 @@ class BandGridSolver:
     channel plane) -- ``fpie_b200.band.CudaBandCore`` adapts ``GridSolver``.
     ``dist`` is ``torch.distributed`` (or any object with the same
     ``batch_isend_irecv / P2POp / isend / irecv / all_reduce`` surface).
+    The default halo of 24 rows is a multiple of both blocking depths the
+    solver picks by itself (8 and 12 sweeps per pass), so an exchange interval
+    never ends in a short pass.
     """
 
-    def __init__(self, core, dist, group=None, halo: int = 16):
+    def __init__(self, core, dist, group=None, halo: int = 24):
         self.core, self.dist, self.group = core, dist, group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
@@ -223,7 +226,7 @@ class BandGridProcessor:
     problem, mpi/grid.cc:34-54) every rank takes the uint8 images and keeps only its slab; ``step``
     returns the full blended target on rank 0 and ``None`` elsewhere (process.py:388-395)."""
 
-    def __init__(self, gradient: str = "max", core=None, dist=None, group=None, halo: int = 16):
+    def __init__(self, gradient: str = "max", core=None, dist=None, group=None, halo: int = 24):
         self.gradient = gradient
         self.solver = BandGridSolver(core, dist, group, halo)
         self.dist, self.group = dist, group

@@ -41,6 +41,7 @@ def main():
                 continue
             core.reset_from_images(src, mask, tgt, (0, 0), (0, 0), "max")
             info = core.info()
+            k = k or info["block_k"]  # k = 0: whatever the solver chose for this grid
             iters = args.iters // k * k
             core.sweeps_async(iters)
             torch.cuda.synchronize()
