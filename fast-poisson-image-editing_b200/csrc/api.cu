@@ -96,6 +96,14 @@ API int fpie_b200_grid_step_into(fpie_b200_grid *g, int iters, uint8_t *dst, int
   NEED(g);
   return guarded([&] { g->impl.step(iters, dst, out_err3, dst_row_stride); });
 }
+API int fpie_b200_grid_solve(fpie_b200_grid *g, int max_iters, int check_every, float tol, float *out_err3,
+                             int *iters_done) {
+  NEED(g);
+  return guarded([&] {
+    const int done = g->impl.solve(max_iters, check_every, tol, out_err3);
+    if (iters_done) *iters_done = done;
+  });
+}
 API int fpie_b200_grid_state(fpie_b200_grid *g, float *out_state) {
   NEED(g);
   return guarded([&] { g->impl.state(out_state); });
@@ -197,6 +205,14 @@ API int fpie_b200_equ_step(fpie_b200_equ *e, int iters, uint8_t *out_img, float 
 API int fpie_b200_equ_state(fpie_b200_equ *e, float *out_state) {
   NEED(e);
   return guarded([&] { e->impl.state(out_state); });
+}
+API int fpie_b200_equ_solve(fpie_b200_equ *e, int max_iters, int check_every, float tol, float *out_err3,
+                            int *iters_done) {
+  NEED(e);
+  return guarded([&] {
+    const int done = e->impl.solve(max_iters, check_every, tol, out_err3);
+    if (iters_done) *iters_done = done;
+  });
 }
 API int fpie_b200_equ_sweeps_async(fpie_b200_equ *e, int iters) {
   NEED(e);

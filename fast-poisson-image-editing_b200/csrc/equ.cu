@@ -670,6 +670,26 @@ void EquSolver::fetch(uint8_t *out_img, float *out_err3) {
     for (int c = 0; c < 3; ++c) out_err3[c] = (float)host_err_[c];
 }
 
+// Sweep until every channel's residual is <= tol (checked every `check_every` sweeps) or `max_iters`
+// sweeps have run (red-black mode: one "sweep" = both half sweeps, as in step()).
+int EquSolver::solve(int max_iters, int check_every, float tol, float *out_err3) {
+  require_ready();
+  FPIE_REQUIRE(max_iters >= 0 && check_every >= 1, "solve: max_iters must be >= 0 and check_every >= 1");
+  int done = 0;
+  while (true) {
+    finish_async();
+    sync();
+    const double worst = std::max(host_err_[0], std::max(host_err_[1], host_err_[2]));
+    if (worst <= (double)tol || done >= max_iters) break;
+    const int s = std::min(check_every, max_iters - done);
+    sweeps_async(s);
+    done += s;
+  }
+  if (out_err3)
+    for (int c = 0; c < 3; ++c) out_err3[c] = (float)host_err_[c];
+  return done;
+}
+
 void EquSolver::step(int iters, uint8_t *out_img, float *out_err3) {
   sweeps_async(iters);
   finish_async();

@@ -29,6 +29,7 @@ class EquSolver {
   void sync();
   void fetch(uint8_t *out_img, float *out_err3);
   void step(int iters, uint8_t *out_img, float *out_err3);
+  int solve(int max_iters, int check_every, float tol, float *out_err3);
   void step_paste(int iters, uint8_t *out_crop, float *out_err3, int64_t row_stride = 0);
   void state(float *out);
   void system(int32_t *out_A, float *out_X, float *out_B);

@@ -1217,6 +1217,27 @@ void GridSolver::fetch(uint8_t *out_img, float *out_err3, int64_t row_stride) {
   }
 }
 
+// Sweep until every channel's residual is <= tol (checked every `check_every` sweeps) or `max_iters`
+// sweeps have run.  The state stays on the device; step(0) afterwards returns image and err.
+int GridSolver::solve(int max_iters, int check_every, float tol, float *out_err3) {
+  require_ready();
+  FPIE_REQUIRE(max_iters >= 0 && check_every >= 1, "solve: max_iters must be >= 0 and check_every >= 1");
+  FPIE_REQUIRE(batch_.batch == 0, "solve: not available for batched patches (per-patch residuals)");
+  int done = 0;
+  while (true) {
+    finish_async();
+    sync();
+    const double worst = std::max(host_err_[0], std::max(host_err_[1], host_err_[2]));
+    if (worst <= (double)tol || done >= max_iters) break;
+    const int s = std::min(check_every, max_iters - done);
+    sweeps_async(s);
+    done += s;
+  }
+  if (out_err3)
+    for (int c = 0; c < 3; ++c) out_err3[c] = (float)host_err_[c];
+  return done;
+}
+
 void GridSolver::step(int iters, uint8_t *out_img, float *out_err3, int64_t row_stride) {
   sweeps_async(iters);
   finish_async();

@@ -65,6 +65,7 @@ class GridSolver {
   void sync();
   void fetch(uint8_t *out_img, float *out_err3, int64_t row_stride = 0);
   void step(int iters, uint8_t *out_img, float *out_err3, int64_t row_stride = 0);
+  int solve(int max_iters, int check_every, float tol, float *out_err3);
   void state(float *out);
   void set_row_window(int lo, int hi);
   void band_view(int which, float **base, int64_t *plane_stride, int64_t *row_pitch, int *pad_rows, int *pad_cols);

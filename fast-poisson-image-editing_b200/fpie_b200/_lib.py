@@ -30,6 +30,7 @@ SIGNATURES = {
     "fpie_b200_grid_reset": [c_void_p, c_int, c_int, i32p, c_i64, c_i64, f32p, f32p],
     "fpie_b200_grid_step": [c_void_p, c_int, u8p, f32p],
     "fpie_b200_grid_step_into": [c_void_p, c_int, u8p, c_i64, f32p],
+    "fpie_b200_grid_solve": [c_void_p, c_int, c_int, ctypes.c_float, f32p, intp],
     "fpie_b200_grid_state": [c_void_p, f32p],
     "fpie_b200_grid_sweeps_async": [c_void_p, c_int],
     "fpie_b200_grid_finish_async": [c_void_p],
@@ -49,6 +50,7 @@ SIGNATURES = {
     "fpie_b200_equ_partition": [c_void_p, c_int, c_int, i32p, c_i64, c_i64, i32p],
     "fpie_b200_equ_reset": [c_void_p, c_i64, i32p, f32p, f32p],
     "fpie_b200_equ_step": [c_void_p, c_int, u8p, f32p],
+    "fpie_b200_equ_solve": [c_void_p, c_int, c_int, ctypes.c_float, f32p, intp],
     "fpie_b200_equ_state": [c_void_p, f32p],
     "fpie_b200_equ_sweeps_async": [c_void_p, c_int],
     "fpie_b200_equ_finish_async": [c_void_p],

@@ -44,6 +44,13 @@ class BaseProcessor:
     def sync(self) -> None:
         self.core.sync()
 
+    def solve(self, max_iters: int, tol: float, check_every: int = 100):
+        """Convergence-driven ``step``: sweep until ``max(err) <= tol`` or ``max_iters``; returns
+        ``(tgt, err, iterations_run)`` (not part of the reference Processor)."""
+        _, done = self.core.solve(max_iters, tol, check_every)
+        out, err = self.step(0)
+        return out, err, done
+
     def _reset_with_canvas(self, tgt, device_reset):
         """Run the device-side reset while a worker thread makes the Processor's private copy of
         the target (process.py:268 / 384); both release the GIL, so they overlap."""

@@ -134,6 +134,19 @@ class GridSolver(_Handle):
         return img, err
 
     # -- extras ---------------------------------------------------------------
+    def solve(self, max_iters: int, tol: float, check_every: int = 100):
+        """Sweep until every channel of ``err`` is ``<= tol`` (looked at every
+        ``check_every`` sweeps) or ``max_iters`` sweeps have run; returns
+        ``(err, iterations_run)``.  The state stays on the device: ``step(0)``
+        returns the image.  Never implied by ``step`` -- the reference always runs
+        the iteration count it is given."""
+        self._need_shape()
+        err = np.empty(3, np.float32)
+        done = ctypes.c_int(0)
+        _lib.check(self._lib.fpie_b200_grid_solve(self.handle, int(max_iters), int(check_every), float(tol),
+                                                  _ptr(err, ctypes.c_float), ctypes.byref(done)))
+        return err, done.value
+
     def step_into(self, iteration: int, canvas: np.ndarray, x0: int, y0: int) -> np.ndarray:
         """``step`` whose uint8 result lands directly in ``canvas[x0:x0+n, y0:y0+m]``
         (a C-contiguous uint8 ``[rows, cols, 3]`` image); returns ``err``."""
@@ -355,6 +368,15 @@ class EquSolver(_Handle):
         _lib.check(self._lib.fpie_b200_equ_step_paste(self.handle, int(iteration), _ptr(crop, ctypes.c_uint8),
                                                       _ptr(err, ctypes.c_float)))
         return crop, err
+
+    def solve(self, max_iters: int, tol: float, check_every: int = 100):
+        """As ``GridSolver.solve``: sweep until ``max(err) <= tol`` or ``max_iters``;
+        returns ``(err, iterations_run)``."""
+        err = np.empty(3, np.float32)
+        done = ctypes.c_int(0)
+        _lib.check(self._lib.fpie_b200_equ_solve(self.handle, int(max_iters), int(check_every), float(tol),
+                                                 _ptr(err, ctypes.c_float), ctypes.byref(done)))
+        return err, done.value
 
     def step_paste_into(self, iteration: int, canvas: np.ndarray, x0: int, y0: int) -> np.ndarray:
         """``step_paste`` landing directly in ``canvas[x0:x0+n, y0:y0+m]`` (C-contiguous uint8 image)."""

@@ -89,6 +89,14 @@ int fpie_b200_grid_step(fpie_b200_grid *g, int iters, uint8_t *out_img, float *o
  * paste `tgt[x0:x1, y0:y1] = img` (fpie/process.py:393) done by the copy engine. */
 int fpie_b200_grid_step_into(fpie_b200_grid *g, int iters, uint8_t *dst, int64_t dst_row_stride, float *out_err3);
 
+/* Convergence-driven stepping (the reference only offers a fixed
+ * iteration count, fpie/cli.py:46-61 prints err every -p sweeps and leaves the decision to the user):
+ * run sweeps in chunks of `check_every` until every channel of err (the quantity step() returns) is
+ * <= tol, or `max_iters` sweeps have run.  Never the default; the state stays on the device and a
+ * following step(0) returns the image.  *iters_done = sweeps actually run. */
+int fpie_b200_grid_solve(fpie_b200_grid *g, int max_iters, int check_every, float tol, float *out_err3,
+                         int *iters_done);
+
 /* The fp32 state [n, m, 3] (the reference never exposes it from native
  * cores; needed for the fp32 parity check). */
 int fpie_b200_grid_state(fpie_b200_grid *g, float *out_state);
@@ -190,6 +198,8 @@ int fpie_b200_equ_reset(fpie_b200_equ *e, int64_t N, const int32_t *A, const flo
  * true Jacobi (np_solver.py:33-50 semantics). */
 int fpie_b200_equ_step(fpie_b200_equ *e, int iters, uint8_t *out_img, float *out_err3);
 int fpie_b200_equ_state(fpie_b200_equ *e, float *out_state);
+/* Convergence-driven stepping, as fpie_b200_grid_solve (red-black mode: one sweep = both half sweeps). */
+int fpie_b200_equ_solve(fpie_b200_equ *e, int max_iters, int check_every, float tol, float *out_err3, int *iters_done);
 
 int fpie_b200_equ_sweeps_async(fpie_b200_equ *e, int iters);
 int fpie_b200_equ_finish_async(fpie_b200_equ *e);

@@ -6,7 +6,7 @@ import pytest
 from hypothesis import HealthCheck, given, settings
 from hypothesis import strategies as st
 
-from oracle import np_oracle
+from oracle import c_oracle, np_oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -77,3 +77,70 @@ def test_processor_matches_oracle(blend, kind):
         np.testing.assert_array_equal(state, orc.t if kind == "grid" else orc.X)
         np.testing.assert_array_equal(out, wout)
         np.testing.assert_allclose(err, werr, rtol=1e-4, atol=1e-3)
+
+
+# -- convergence-driven stepping --------------------------
+def _oracle_solve(step_fn, err_fn, max_iters, check_every, tol):
+    """What solve() is defined to do, on the oracle: check, then sweep in chunks."""
+    done = 0
+    while True:
+        if err_fn().max() <= tol or done >= max_iters:
+            return done
+        s = min(check_every, max_iters - done)
+        step_fn(s)
+        done += s
+
+
+@pytest.mark.parametrize("solver_kind", ["grid", "equ", "equ-gather", "equ-redblack"])
+def test_solve_stops_where_the_oracle_stops(solver_kind):
+    import fpie_b200
+    from fpie_b200 import synth
+
+    src, mask, tgt = synth.make_problem("circle", 150, 170, seed=11)
+    check_every, max_iters = 25, 400
+    if solver_kind == "grid":
+        proc = fpie_b200.GridProcessor("max", "b200")
+        ora = np_oracle.GridOracle("max")
+        ora.reset(src, mask, tgt, (0, 0), (0, 0))
+        sweep = lambda s: setattr(ora, "t", c_oracle.grid_sweeps(ora.mask, ora.t, ora.g, s))  # noqa: E731
+        err_of = lambda: np_oracle.grid_residual_f64(ora.mask, ora.t, ora.g)  # noqa: E731
+    else:
+        mode = {"equ": "jacobi", "equ-gather": "gather", "equ-redblack": "redblack"}[solver_kind]
+        proc = fpie_b200.EquProcessor("max", "b200", mode=mode)
+    proc.reset(src, mask, tgt, (0, 0), (0, 0))
+    if solver_kind != "grid":
+        A, X, B = proc.core.system()
+        state = {"x": X.copy()}
+        if mode == "redblack":
+            m_full, (x0, x1, y0, y1) = np_oracle.canonical_mask(mask)
+            n_mid = np_oracle.partition_redblack(m_full[x0:x1, y0:y1])[1]
+            sweep = lambda s: state.__setitem__("x", np_oracle.equ_sweeps_redblack(A, state["x"], B, s, n_mid))  # noqa: E731
+        else:
+            sweep = lambda s: state.__setitem__("x", c_oracle.equ_sweeps(A, state["x"], B, s))  # noqa: E731
+        err_of = lambda: np_oracle.equ_residual_f64(A, state["x"], B)  # noqa: E731
+
+    # residuals at every check point; pick tolerances between two of them so that rounding in the
+    # last digit of err cannot move the stopping point
+    errs = [err_of().max()]
+    for _ in range(max_iters // check_every):
+        sweep(check_every)
+        errs.append(err_of().max())
+    assert errs[3] > errs[6] > errs[10]
+    for stop_at in (3, 6, 10):
+        tol = float(np.sqrt(errs[stop_at] * errs[stop_at - 1]))
+        proc.reset(src, mask, tgt, (0, 0), (0, 0))
+        if solver_kind != "grid":
+            state["x"] = X.copy()
+        out, err, done = proc.solve(max_iters, tol, check_every)
+        assert done == stop_at * check_every
+        np.testing.assert_allclose(err.max(), errs[stop_at], rtol=1e-4)
+        assert err.max() <= tol
+        out2, err2 = proc.step(0)
+        np.testing.assert_array_equal(out, out2)
+    # never converging within the budget: runs exactly max_iters; zero budget: runs nothing
+    proc.reset(src, mask, tgt, (0, 0), (0, 0))
+    assert proc.solve(60, 0.0, 25)[2] == 60
+    proc.reset(src, mask, tgt, (0, 0), (0, 0))
+    assert proc.solve(0, 0.0, 25)[2] == 0
+    with pytest.raises(RuntimeError):
+        proc.core.solve(10, 1.0, 0)
