@@ -96,6 +96,10 @@ API int fpie_b200_grid_step_into(fpie_b200_grid *g, int iters, uint8_t *dst, int
   NEED(g);
   return guarded([&] { g->impl.step(iters, dst, out_err3, dst_row_stride); });
 }
+API int fpie_b200_grid_set_formulation(fpie_b200_grid *g, int equ) {
+  NEED(g);
+  return guarded([&] { g->impl.set_formulation(equ != 0); });
+}
 API int fpie_b200_grid_solve(fpie_b200_grid *g, int max_iters, int check_every, float tol, float *out_err3,
                              int *iters_done) {
   NEED(g);

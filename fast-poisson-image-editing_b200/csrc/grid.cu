@@ -572,7 +572,7 @@ grid_to_u8_kernel(PlaneGeom g, BatchMap bm, const float *__restrict__ x, uint8_t
 // consecutive plane columns of one crop row -- mask word by ballot, state from
 // the target crop, quarter-scaled mixed gradient on masked pixels.
 __global__ void __launch_bounds__(256)
-grid_build_kernel(PlaneGeom g, BlendImages b, uint32_t *__restrict__ bits, float *__restrict__ x0,
+grid_build_kernel(PlaneGeom g, BlendImages b, int equ_form, uint32_t *__restrict__ bits, float *__restrict__ x0,
                   float *__restrict__ x1, float *__restrict__ hq, unsigned long long *__restrict__ count) {
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -592,6 +592,34 @@ grid_build_kernel(PlaneGeom g, BlendImages b, uint32_t *__restrict__ bits, float
   }
   if (!inside) return;
   const long long off = prow * g.pitch + pcol;
+  if (equ_form) {
+    // EquSolver arithmetic on the grid (the promoted form, see grid_from_equ_kernel): an unknown carries
+    // X = target and B = grad + sum of the targets of its neighbours OUTSIDE the mask (process.py:255-263;
+    // small integers and halves: exact in any order); every other pixel is the constant 0 (A's row 0).
+    // In slab mode the halo frame rows hold the neighbour band's unknowns: live state, cleared mask bit.
+    const int mr = pb.x0 + pr, mc2 = pb.y0 + pc2;
+    const bool live = pb.slab ? raw_mask_at(pb, mr, mc2) : on;
+    const int dr[4] = {-1, 1, 0, 0}, dc[4] = {0, 0, -1, 1};
+    bool outside[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      outside[k] = on && !(pb.slab ? raw_mask_at(pb, mr + dr[k], mc2 + dc[k]) : canonical_mask_at(pb, mr + dr[k], mc2 + dc[k]));
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const float t = live ? target_at(pb, pr, pc2, ch) : 0.f;
+      float bsum = 0.f;
+      if (on) {
+        bsum = pixel_gradient(pb, pr, pc2, ch);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (outside[k]) bsum += target_at(pb, pr + dr[k], pc2 + dc[k], ch);
+      }
+      x0[ch * g.plane + off] = t;
+      x1[ch * g.plane + off] = t;
+      hq[ch * g.plane + off] = 0.25f * bsum;
+    }
+    return;
+  }
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
     const float t = target_at(pb, pr, pc2, ch);
@@ -851,6 +879,7 @@ void GridSolver::export_to_equ(const EquEmbed &e) {
 
 void GridSolver::build_from_upload() {
   const BlendImages &b = upload_.images();
+  FPIE_REQUIRE(!(equ_form_ && b.batch > 0), "the EquSolver formulation is not available for batched patches");
   layout(b.n, b.m);
   const PlaneGeom &g = geom_;
   for (auto &buf : x_) buf.resize((size_t)g.plane * 3);
@@ -864,7 +893,8 @@ void GridSolver::build_from_upload() {
   CUDA_CHECK(cudaMemsetAsync(err_.ptr, 0, err_.bytes(), stream_));
   const long long warps = (long long)g.n * g.wpitch;
   grid_build_kernel<<<blocks_for(warps * 32, 256), 256, 0, stream_>>>(
-      g, b, bits_.ptr, x_[0].ptr, x_[1].ptr, hq_.ptr, reinterpret_cast<unsigned long long *>(err_.ptr + 3));
+      g, b, equ_form_ ? 1 : 0, bits_.ptr, x_[0].ptr, x_[1].ptr, hq_.ptr,
+      reinterpret_cast<unsigned long long *>(err_.ptr + 3));
   CUDA_CHECK(cudaGetLastError());
   stats_.launches += 2;
   after_state_loaded();

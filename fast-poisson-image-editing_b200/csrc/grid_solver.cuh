@@ -68,6 +68,8 @@ class GridSolver {
   int solve(int max_iters, int check_every, float tol, float *out_err3);
   void state(float *out);
   void set_row_window(int lo, int hi);
+  // image-level resets build the EquSolver's system on the grid (boundary folded into B, zero outside the mask)
+  void set_formulation(bool equ) { equ_form_ = equ; }
   void band_view(int which, float **base, int64_t *plane_stride, int64_t *row_pitch, int *pad_rows, int *pad_cols);
 
   int device() const { return device_; }
@@ -92,6 +94,7 @@ class GridSolver {
   int block_k_;
   int halo_x_;
   int variant_;
+  bool equ_form_ = false;
   bool auto_tune_ = false;  // tile shape chosen at reset
   bool auto_k_ = false;     // blocking depth chosen at reset
   int sm_count_ = 0;

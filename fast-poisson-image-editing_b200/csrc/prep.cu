@@ -111,6 +111,7 @@ void BlendUpload::upload(cudaStream_t stream, const uint8_t *src, int sh, int sw
   b.sh = sh; b.sw = sw; b.mh = mh; b.mw = mw; b.mc = mc; b.th = th; b.tw = tw;
   b.h0 = h0; b.w0 = w0; b.h1 = h1; b.w1 = w1;
   b.mode = mode;
+  b.slab = crop ? 0 : 1;
   if (!crop) {
     // slab mode (row-band sharding): the whole mask image is the grid; its own frame acts as the
     // fixed boundary (global frame rows, or halo rows refreshed by the neighbour band)

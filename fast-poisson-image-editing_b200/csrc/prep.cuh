@@ -22,6 +22,9 @@ struct BlendImages {
   // batch mode (batch > 0): src / mask / tgt hold `batch` patches of mh x mw pixels back to back;
   // the grid is a mosaic of bcols patches per row, each patch keeping its own fixed frame
   int batch, bcols;
+  // slab mode (row-band sharding): the mask image is already the canonical crop of the global mask and
+  // the whole image is the grid; its first / last rows are halo rows, not a real frame
+  int slab;
 };
 
 // Batch mosaic geometry shared by the output kernels (batch == 0: plain image).
@@ -57,6 +60,16 @@ class BlendUpload {
 // (mean(-1) >= 128  <=>  sum >= 128 * channels, exact) and a cleared 1-px frame.
 __device__ __forceinline__ bool canonical_mask_at(const BlendImages &b, int r, int c) {
   if (r <= 0 || c <= 0 || r >= b.mh - 1 || c >= b.mw - 1) return false;
+  const uint8_t *p = b.mask + ((long long)r * b.mw + c) * b.mc;
+  int s = 0;
+  for (int k = 0; k < b.mc; ++k) s += (int)p[k];
+  return s >= 128 * b.mc;
+}
+
+// the thresholded mask bit without the cleared frame (inside the image only): in slab mode this is what
+// the pixel is in the GLOBAL mask, also on the slab's halo frame rows
+__device__ __forceinline__ bool raw_mask_at(const BlendImages &b, int r, int c) {
+  if (r < 0 || c < 0 || r >= b.mh || c >= b.mw) return false;
   const uint8_t *p = b.mask + ((long long)r * b.mw + c) * b.mc;
   int s = 0;
   for (int k = 0; k < b.mc; ++k) s += (int)p[k];

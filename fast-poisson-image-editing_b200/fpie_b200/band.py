@@ -253,6 +253,7 @@ class BandGridProcessor:
         )
         self.box = (to[0], to[0] + n, to[1], to[1] + m)
         self.tgt = np.array(tgt, dtype=np.uint8, copy=True) if self.root else None
+        self._crop_mask = crop_mask
         return n * m
 
     def sync(self) -> None:
@@ -275,11 +276,40 @@ class BandGridProcessor:
         self.dist.gather(padded, parts, dst=0, group=self.group)
         if not self.root:
             return None
-        x0, _, y0, y1 = self.box
         for i in range(world):
             rows = off[i + 1] - off[i]
-            self.tgt[x0 + off[i] : x0 + off[i + 1], y0:y1] = parts[i][:rows].cpu().numpy()
+            self._paste(off[i], off[i + 1], parts[i][:rows].cpu().numpy())
         return self.tgt, err
+
+    def _paste(self, lo: int, hi: int, band_img: np.ndarray) -> None:
+        """Rows [lo, hi) of the solved crop -> the full target (process.py:393)."""
+        x0, _, y0, y1 = self.box
+        self.tgt[x0 + lo : x0 + hi, y0:y1] = band_img
+
+
+class BandEquProcessor(BandGridProcessor):
+    """``EquProcessor`` interface over row bands.
+
+    The EquSolver's gather is all-to-all for arbitrary ids (the reference's MPI EquSolver broadcasts
+    the whole vector every few sweeps, mpi/equ.cc:136-146); on row-major ids, though, unknown i only
+    reads unknowns of the rows above and below, and the system IS a grid problem: state ``X`` on the
+    masked pixels and 0 elsewhere, gradient ``B`` (the form ``EquSolver`` promotes to on one GPU).
+    Built directly from the uint8 slab on each rank, it shards by row bands exactly like the
+    GridSolver and returns the EquSolver's numbers: same fp32 state, same uint8 image, ``reset``
+    returns ``K + 1`` and ``step`` scatters only the K solved pixels (process.py:273-280)."""
+
+    def __init__(self, gradient: str = "max", core=None, dist=None, group=None, halo: int = 24):
+        super().__init__(gradient, core, dist, group, halo)
+        self.solver.core.set_formulation(True)
+
+    def reset(self, src, mask, tgt, mask_on_src=(0, 0), mask_on_tgt=(0, 0)) -> int:
+        super().reset(src, mask, tgt, mask_on_src, mask_on_tgt)
+        return int(np.count_nonzero(self._crop_mask)) + 1  # max_id (process.py:190)
+
+    def _paste(self, lo: int, hi: int, band_img: np.ndarray) -> None:
+        x0, _, y0, y1 = self.box
+        on = self._crop_mask[lo:hi] > 0
+        self.tgt[x0 + lo : x0 + hi, y0:y1][on] = band_img[on]
 
 
 class _DeviceRows:
@@ -306,6 +336,9 @@ class CudaBandCore:
     def reset_slab(self, src, mask, tgt, gradient):
         self.solver.reset_slab(src, mask, tgt, gradient)
         self._views.clear()
+
+    def set_formulation(self, equ: bool):
+        self.solver.set_formulation(equ)
 
     def sweeps_async(self, k):
         self.solver.sweeps_async(k)

@@ -134,6 +134,12 @@ class GridSolver(_Handle):
         return img, err
 
     # -- extras ---------------------------------------------------------------
+    def set_formulation(self, equ: bool) -> None:
+        """Image-level resets that follow build the EquSolver's system on the grid
+        (``equ=True``: X / B of process.py:227-266, zero outside the mask) instead of
+        the GridSolver's -- the row-band shardable form of the EquSolver."""
+        _lib.check(self._lib.fpie_b200_grid_set_formulation(self.handle, 1 if equ else 0))
+
     def solve(self, max_iters: int, tol: float, check_every: int = 100):
         """Sweep until every channel of ``err`` is ``<= tol`` (looked at every
         ``check_every`` sweeps) or ``max_iters`` sweeps have run; returns

@@ -158,6 +158,14 @@ int fpie_b200_grid_band_current(fpie_b200_grid *g, int *which_buffer);
  * [row_lo, row_hi) -- a band counts only its own rows, not its halo. */
 int fpie_b200_grid_set_row_window(fpie_b200_grid *g, int row_lo, int row_hi);
 
+/* Formulation built by the image-level resets (reset_from_images / reset_slab) that follow:
+ * 0 (default) = GridSolver's (unmasked pixels hold the target, fpie/process.py:354-378);
+ * 1 = EquSolver's, laid out on the grid: unknowns carry X = target and B = grad + the targets of
+ * their neighbours outside the mask (fpie/process.py:227-266), every other pixel the constant 0 --
+ * the arithmetic of np_solver.py:33-41 on row-major ids, i.e. what EquSolver computes, in a form
+ * that shards by row bands. */
+int fpie_b200_grid_set_formulation(fpie_b200_grid *g, int equ);
+
 /* ---- EquSolver ----------------------------------------------------------
  * Replaces CudaEquSolver (fpie/core/cuda/equ.cu:7-211) behind the EquSolver
  * interface of fpie/core/base_solver.h:12-75. */

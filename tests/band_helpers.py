@@ -17,6 +17,10 @@ class OracleBandCore:
     CUDA GridSolver does to a slab."""
 
     torch_device = "cpu"
+    equ_form = False
+
+    def set_formulation(self, equ):
+        self.equ_form = bool(equ)
 
     def reset(self, N, mask, tgt, grad):
         m = np.array(mask, np.int32, copy=True)
@@ -36,6 +40,20 @@ class OracleBandCore:
         n, w = m.shape
         grad = np_oracle._pixel_gradient(gradient, src, tgt, (0, 0), (0, 0), (n, w))
         grad[m == 0] = 0
+        if self.equ_form:
+            # the EquSolver's system on the grid (process.py:227-266): B = grad + targets of the neighbours
+            # outside the GLOBAL mask; X = target on globally masked pixels (also on the halo frame rows,
+            # which hold the neighbour band's unknowns), 0 elsewhere
+            raw = np.asarray(mask).reshape(n, w, -1).mean(-1) >= 128
+            t = tgt.astype(np.float32)
+            pad_raw = np.pad(raw, 1)
+            pad_t = np.pad(t, ((1, 1), (1, 1), (0, 0)))
+            for dr, dc in ((-1, 0), (1, 0), (0, -1), (0, 1)):
+                nb_raw = pad_raw[1 + dr : 1 + dr + n, 1 + dc : 1 + dc + w]
+                nb_t = pad_t[1 + dr : 1 + dr + n, 1 + dc : 1 + dc + w]
+                grad += np.where((m > 0) & ~nb_raw, 1.0, 0.0)[:, :, None].astype(np.float32) * nb_t
+            self.reset(n * w, m, t * raw[:, :, None], grad)
+            return
         self.reset(n * w, m, tgt.astype(np.float32), grad)
 
     def _aos(self):

@@ -141,6 +141,61 @@ def test_gloo_band_processor_matches_single_processor(tmp_path):
     np.testing.assert_allclose(z["err"], werr, rtol=1e-5)
 
 
+def _equ_proc_worker(rank, world, port, out_dir):
+    for p in (ROOT, PKG_ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from band_helpers import OracleBandCore
+
+    from fpie_b200 import band, synth
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        src, mask, tgt = synth.make_problem("holes", 110, 96, seed=9)
+        big_tgt = np.random.default_rng(2).integers(0, 256, (140, 120, 3), dtype=np.uint8)
+        proc = band.BandEquProcessor("max", OracleBandCore(), dist, halo=5)
+        n = proc.reset(src, mask, big_tgt, (0, 0), (17, 11))
+        proc.sync()
+        proc.step(9)
+        res = proc.step(14)
+        state = proc.solver.band_state()
+        p = proc.solver.plan
+        np.savez(os.path.join(out_dir, f"equ{rank}.npz"), state=state, lo=p.band_lo, hi=p.band_hi, n=n,
+                 out=res[0] if rank == 0 else 0, err=res[1] if rank == 0 else 0)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_band_equ_processor_matches_single_equ_processor(tmp_path):
+    """Row-band sharded EquSolver arithmetic == the oracle's single-domain EquProcessor: same fp32
+    unknowns (bit for bit), same uint8 image, same N, err within tolerance."""
+    world = 3
+    mp.spawn(_equ_proc_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    from fpie_b200 import synth
+
+    src, mask, tgt = synth.make_problem("holes", 110, 96, seed=9)
+    big_tgt = np.random.default_rng(2).integers(0, 256, (140, 120, 3), dtype=np.uint8)
+    want = np_oracle.EquOracle("max")
+    n = want.reset(src, mask, big_tgt, (0, 0), (17, 11))
+    want.step(9)
+    wout, werr = want.step(14)
+    m_full, (x0, x1, y0, y1) = np_oracle.canonical_mask(mask)
+    crop = m_full[x0:x1, y0:y1]
+    ids = np_oracle.partition_rowmajor(crop)
+    z0 = np.load(tmp_path / "equ0.npz")
+    assert int(z0["n"]) == n
+    np.testing.assert_array_equal(z0["out"], wout)
+    np.testing.assert_allclose(z0["err"], werr, rtol=1e-4)
+    for r in range(world):
+        z = np.load(tmp_path / f"equ{r}.npz")
+        lo, hi = int(z["lo"]), int(z["hi"])
+        on = crop[lo:hi] > 0
+        np.testing.assert_array_equal(z["state"][on], want.X[ids[lo:hi][on]])  # unknowns, bit for bit
+        assert not z["state"][~on].any()  # everything else is the constant 0
+
+
 def test_canonical_crop_matches_oracle():
     from fpie_b200 import band, synth
 

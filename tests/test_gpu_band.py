@@ -144,6 +144,70 @@ def test_thread_band_processor_image_level():
     np.testing.assert_allclose(err, werr, rtol=1e-4)
 
 
+@pytest.mark.parametrize("kind,world,halo", [("star", 3, 16), ("holes", 2, 24), ("ring", 4, 8)])
+def test_thread_band_equ_processor_matches_single_gpu_equ_solver(kind, world, halo):
+    """BandEquProcessor (EquSolver arithmetic on row bands) == EquProcessor on one GPU: same unknowns
+    bit for bit, same blended image, same N; err within tolerance."""
+    import torch
+
+    import fpie_b200
+    from fpie_b200 import band, synth
+
+    src, mask, tgt = synth.make_problem(kind, 610, 540, seed=5)
+    big_tgt = np.random.default_rng(8).integers(0, 256, (700, 640, 3), dtype=np.uint8)
+    single = fpie_b200.EquProcessor("max", "b200")
+    n = single.reset(src, mask, big_tgt, (0, 0), (31, 52))
+    single.step(30)
+    wout, werr = single.step(45)
+    wout = wout.copy()
+    wstate = single.core.state()
+    dist = ThreadDist(world)
+    results, errors = [None] * world, []
+
+    def work(rank):
+        try:
+            dist.bind(rank)
+            torch.cuda.set_device(0)
+            proc = band.BandEquProcessor("max", band.CudaBandCore(fpie_b200.GridSolver(8, 8, device=0)), dist, halo=halo)
+            got_n = proc.reset(src, mask, big_tgt, (0, 0), (31, 52))
+            proc.sync()
+            proc.step(30)
+            res = proc.step(45)
+            results[rank] = (got_n, res, proc.solver.plan, proc.solver.band_state())
+        except Exception as exc:
+            errors.append(exc)
+            try:
+                dist.bar.abort()
+            except Exception:
+                pass
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    m_full, (x0, x1, y0, y1) = np_oracle.canonical_mask(mask)
+    crop = m_full[x0:x1, y0:y1]
+    ids = np_oracle.partition_rowmajor(crop)
+    assert results[0][0] == n
+    out, err = results[0][1]
+    np.testing.assert_array_equal(out, wout)
+    # random holes leave tiny domains that converge to rounding noise within 75 sweeps; the residual is
+    # then a sum of last-bit residues, which the two expression orders (|4t-g-U-D-L-R| on the grid,
+    # |B+sum(X[A])-4X| in the EquSolver) round differently
+    np.testing.assert_allclose(err, werr, rtol=1e-4 if kind != "holes" else 0.1)
+    for got_n, res, plan, state in results:
+        on = crop[plan.band_lo : plan.band_hi] > 0
+        np.testing.assert_array_equal(state[on], wstate[ids[plan.band_lo : plan.band_hi][on]])
+    # and against the CPU oracle of the EquSolver
+    want = np_oracle.EquOracle("max")
+    want.reset(src, mask, big_tgt, (0, 0), (31, 52))
+    want.X = c_oracle.equ_sweeps(want.A, want.X, want.B, 75)
+    np.testing.assert_array_equal(wstate, want.X)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
