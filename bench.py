@@ -432,7 +432,7 @@ def run_band(args, work, name):
     plan = band.make_plan(n, world, rank, halo)
     src, mask, tgt, unknowns = slab_images(work, plan, n, m, rank)
     core = fpie_b200.GridSolver(8, 8, device=dev, block_k=args.block_k)
-    solver = band.BandGridSolver(band.CudaBandCore(core), dist, halo=halo)
+    solver = band.BandGridSolver(band.CudaBandCore(core), dist, halo=halo, overlap=not args.no_overlap)
     t0 = time.perf_counter()
     solver.reset_slab(n, src, mask, tgt, work["grad"])
     torch.cuda.synchronize()
@@ -511,6 +511,8 @@ def run_band(args, work, name):
                 "sweeps_per_step": iters,
                 "block_k": k,
                 "halo": halo,
+                "exchange": "overlapped with the interior tiles of a pass (second stream)" if solver._split
+                else "between passes",
                 "band_rows": plan.band_hi - plan.band_lo,
                 "l2": "per-GPU slab far exceeds the 126 MB L2; no flush needed",
                 "reset_s": reset_s,
@@ -543,6 +545,8 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--iters", type=int, default=0, help="override sweeps per step")
     ap.add_argument("--block-k", type=int, default=0)
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="row bands: exchange halos between passes instead of beside the interior of a pass")
     ap.add_argument("--halo", type=int, default=24, help="halo depth (rows) of the row-band sharding")
     ap.add_argument("--size", type=int, default=0, help="override the image side")
     ap.add_argument("--cpu-budget", type=float, default=12.0)

@@ -96,6 +96,18 @@ API int fpie_b200_grid_step_into(fpie_b200_grid *g, int iters, uint8_t *dst, int
   NEED(g);
   return guarded([&] { g->impl.step(iters, dst, out_err3, dst_row_stride); });
 }
+API int fpie_b200_grid_set_edge_rows(fpie_b200_grid *g, int rows) {
+  NEED(g);
+  return guarded([&] { g->impl.set_edge_rows(rows); });
+}
+API int fpie_b200_grid_pass_async(fpie_b200_grid *g, int nsweeps, int part) {
+  NEED(g);
+  return guarded([&] { g->impl.pass_async(nsweeps, part); });
+}
+API int fpie_b200_grid_flip(fpie_b200_grid *g) {
+  NEED(g);
+  return guarded([&] { g->impl.flip(); });
+}
 API int fpie_b200_grid_set_formulation(fpie_b200_grid *g, int equ) {
   NEED(g);
   return guarded([&] { g->impl.set_formulation(equ != 0); });

@@ -946,17 +946,23 @@ void GridSolver::build_tiles() {
   std::vector<uint32_t> flags(ntiles);
   CUDA_CHECK(cudaMemcpyAsync(flags.data(), tile_flags_.ptr, ntiles * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));
-  std::vector<int2> list;
+  std::vector<int2> &list = host_tiles_;
+  list.clear();
+  host_tile_row_.clear();
   list.reserve((size_t)ntiles * 3);
   int64_t active = 0;
   for (int t = 0; t < ntiles; ++t) {
     if (!(flags[t] & 1u)) continue;
     ++active;
     const int ty = t / tiles_x, tx = t % tiles_x;
-    for (int ch = 0; ch < 3; ++ch)
+    for (int ch = 0; ch < 3; ++ch) {
       list.push_back(pack_tile(g.padr + ty * step_y - block_k_, g.padc + tx * step_x - halo_x_, ch,
                                (flags[t] & 2u) ? 1 : 0));
+      host_tile_row_.push_back(ty);
+    }
   }
+  edge_rows_ = 0;
+  n_part_[0] = n_part_[1] = 0;
   stats_.active_tiles = active;
   stats_.total_tiles = ntiles;
   n_tile_entries_ = (int)list.size();
@@ -1075,30 +1081,48 @@ VariantInfo variant_info(int v) {
     case 10: return {10, 16, 1, true};
     case 11: return {8, 16, 1, true};
     case 12: return {8, 8, 2, true};
-    case 13: return {7, 24, 1, true};
-    case 14: return {7, 12, 2, true};
-    case 15: return {6, 24, 1, true};
-    case 16: return {6, 28, 1, true};
     case 17: return {15, 12, 1, true};
     // two warps per scheduler: each sub-partition's 16384 registers then allow up to 255 per thread
     case 18: return {20, 8, 1, true};
-    case 19: return {22, 8, 1, true};
-    case 23: return {24, 8, 1, true};
     case 24: return {21, 8, 1, true};
     case 25: return {19, 8, 1, true};
-    case 26: return {18, 8, 1, true};
-    case 27: return {24, 7, 1, true};
-    case 28: return {28, 6, 1, true};
     // four warps per CTA, several CTAs per SM: small tiles for small grids without giving up rows per thread
     case 29: return {16, 4, 2, true};
-    case 35: return {16, 4, 3, true};
     case 36: return {21, 4, 2, true};
     case 37: return {12, 4, 3, true};
-    case 38: return {8, 4, 4, true};
     // packed-pair (FFMA2) kernels: rows = 2 x pair-rows per thread
     case 20: return {14, 12, 1, true};
     case 21: return {16, 12, 1, true};
     case 22: return {12, 12, 1, true};
+    default: throw Error("fpie_b200: unknown grid kernel variant");
+  }
+}
+
+// one pass of the tiled kernel in the register-tile shape `variant` names
+static void launch_variant(int variant, const SweepArgs &a) {
+  switch (variant) {
+    case 39: launch_pipe<14, 12, 1>(a); break;
+    case 2: launch_direct<16, 8>(a); break;
+    case 3: launch_direct<8, 16>(a); break;
+    case 4: launch_direct<16, 12>(a); break;
+    case 5: launch_pipe<16, 12, 1>(a); break;
+    case 6: launch_pipe<16, 6, 2>(a); break;
+    case 7: launch_pipe<14, 6, 2>(a); break;
+    case 8: launch_pipe<12, 8, 2>(a); break;
+    case 9: launch_pipe<12, 14, 1>(a); break;
+    case 10: launch_pipe<10, 16, 1>(a); break;
+    case 11: launch_pipe<8, 16, 1>(a); break;
+    case 12: launch_pipe<8, 8, 2>(a); break;
+    case 17: launch_pipe<15, 12, 1>(a); break;
+    case 18: launch_pipe<20, 8, 1>(a); break;
+    case 24: launch_pipe<21, 8, 1>(a); break;
+    case 25: launch_pipe<19, 8, 1>(a); break;
+    case 29: launch_pipe<16, 4, 2>(a); break;
+    case 36: launch_pipe<21, 4, 2>(a); break;
+    case 37: launch_pipe<12, 4, 3>(a); break;
+    case 20: launch_pair<7, 12>(a); break;
+    case 21: launch_pair<8, 12>(a); break;
+    case 22: launch_pair<6, 12>(a); break;
     default: throw Error("fpie_b200: unknown grid kernel variant");
   }
 }
@@ -1155,47 +1179,73 @@ void GridSolver::sweeps_async(int iters) {
     a.xin = x_[cur_].ptr;
     a.xout = x_[cur_ ^ 1].ptr;
     a.tm_x = &tm_x_[cur_];
-    switch (variant_) {
-      case 39: launch_pipe<14, 12, 1>(a); break;
-      case 2: launch_direct<16, 8>(a); break;
-      case 3: launch_direct<8, 16>(a); break;
-      case 4: launch_direct<16, 12>(a); break;
-      case 5: launch_pipe<16, 12, 1>(a); break;
-      case 6: launch_pipe<16, 6, 2>(a); break;
-      case 7: launch_pipe<14, 6, 2>(a); break;
-      case 8: launch_pipe<12, 8, 2>(a); break;
-      case 9: launch_pipe<12, 14, 1>(a); break;
-      case 10: launch_pipe<10, 16, 1>(a); break;
-      case 11: launch_pipe<8, 16, 1>(a); break;
-      case 12: launch_pipe<8, 8, 2>(a); break;
-      case 13: launch_pipe<7, 24, 1>(a); break;
-      case 14: launch_pipe<7, 12, 2>(a); break;
-      case 15: launch_pipe<6, 24, 1>(a); break;
-      case 16: launch_pipe<6, 28, 1>(a); break;
-      case 17: launch_pipe<15, 12, 1>(a); break;
-      case 18: launch_pipe<20, 8, 1>(a); break;
-      case 19: launch_pipe<22, 8, 1>(a); break;
-      case 23: launch_pipe<24, 8, 1>(a); break;
-      case 24: launch_pipe<21, 8, 1>(a); break;
-      case 25: launch_pipe<19, 8, 1>(a); break;
-      case 26: launch_pipe<18, 8, 1>(a); break;
-      case 27: launch_pipe<24, 7, 1>(a); break;
-      case 28: launch_pipe<28, 6, 1>(a); break;
-      case 29: launch_pipe<16, 4, 2>(a); break;
-      case 35: launch_pipe<16, 4, 3>(a); break;
-      case 36: launch_pipe<21, 4, 2>(a); break;
-      case 37: launch_pipe<12, 4, 3>(a); break;
-      case 38: launch_pipe<8, 4, 4>(a); break;
-      case 20: launch_pair<7, 12>(a); break;
-      case 21: launch_pair<8, 12>(a); break;
-      case 22: launch_pair<6, 12>(a); break;
-      default: throw Error("fpie_b200: unknown grid kernel variant");
-    }
+    launch_variant(variant_, a);
     cur_ ^= 1;
     left -= a.nsweeps;
     stats_.launches += 1;
   }
   CUDA_CHECK(cudaGetLastError());
+}
+
+// ---- split passes (row-band sharding: overlap the halo exchange with the interior of a pass) ----------
+// Tiles whose stored rows intersect the first / last `rows` grid rows form the "edge" part of the tile
+// list, the rest the "interior" part.  pass_async() runs ONE pass (<= block_k sweeps) over one part without
+// flipping the state buffers; the caller runs both parts in the order it needs, then flip().
+void GridSolver::set_edge_rows(int rows) {
+  require_ready();
+  FPIE_REQUIRE(rows >= 0, "set_edge_rows: negative row count");
+  DeviceGuard guard(device_);
+  const int step_y = shape_.tile_h() - 2 * block_k_;
+  std::vector<int2> part[2];
+  for (size_t i = 0; i < host_tiles_.size(); ++i) {
+    const int lo = host_tile_row_[i] * step_y, hi = lo + step_y;  // stored rows of the tile
+    const bool edge = lo < rows || hi > geom_.n - rows;
+    part[edge ? 0 : 1].push_back(host_tiles_[i]);
+  }
+  for (int p = 0; p < 2; ++p) {
+    tiles_part_[p].resize(std::max<size_t>(part[p].size(), 1));
+    n_part_[p] = (int)part[p].size();
+    if (!part[p].empty())
+      CUDA_CHECK(cudaMemcpyAsync(tiles_part_[p].ptr, part[p].data(), part[p].size() * sizeof(int2),
+                                 cudaMemcpyHostToDevice, stream_));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(stream_));  // (the host vectors go out of scope)
+  edge_rows_ = rows;
+}
+
+void GridSolver::pass_async(int nsweeps, int part) {
+  require_ready();
+  FPIE_REQUIRE(part == 0 || part == 1, "pass_async: part must be 0 (edge tiles) or 1 (interior tiles)");
+  FPIE_REQUIRE(nsweeps >= 1 && nsweeps <= block_k_, "pass_async: a pass runs 1..block_k sweeps");
+  FPIE_REQUIRE(edge_rows_ > 0, "pass_async needs set_edge_rows");
+  FPIE_REQUIRE(variant_ != 1, "pass_async: not available for the one-sweep-per-launch kernels");
+  DeviceGuard guard(device_);
+  if (stats_.unknowns == 0 || n_part_[part] == 0) return;
+  SweepArgs a{};
+  a.grid = sm_count_;
+  a.stream = stream_;
+  a.g = geom_;
+  a.bits = bits_.ptr;
+  a.hq = hq_.ptr;
+  a.h16 = h16_ok_;
+  a.tm_h = h16_ok_ ? &tm_h16_ : &tm_h_;
+  a.tm_m = &tm_m_;
+  a.tiles = tiles_part_[part].ptr;
+  a.ntiles = n_part_[part];
+  a.halo_y = block_k_;
+  a.halo_x = halo_x_;
+  a.nsweeps = nsweeps;
+  a.xin = x_[cur_].ptr;
+  a.xout = x_[cur_ ^ 1].ptr;
+  a.tm_x = &tm_x_[cur_];
+  launch_variant(variant_, a);
+  stats_.launches += 1;
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void GridSolver::flip() {
+  require_ready();
+  if (stats_.unknowns > 0) cur_ ^= 1;
 }
 
 void GridSolver::finish_async() {

@@ -68,6 +68,9 @@ class GridSolver {
   int solve(int max_iters, int check_every, float tol, float *out_err3);
   void state(float *out);
   void set_row_window(int lo, int hi);
+  void set_edge_rows(int rows);
+  void pass_async(int nsweeps, int part);
+  void flip();
   // image-level resets build the EquSolver's system on the grid (boundary folded into B, zero outside the mask)
   void set_formulation(bool equ) { equ_form_ = equ; }
   void band_view(int which, float **base, int64_t *plane_stride, int64_t *row_pitch, int *pad_rows, int *pad_cols);
@@ -120,6 +123,12 @@ class GridSolver {
   DeviceBuffer<double> err_;  // [3] residual sums + [1] unknown count (as double)
   DeviceBuffer<int2> tiles_;
   DeviceBuffer<uint32_t> tile_flags_;
+  // edge / interior partition of the tile list (set_edge_rows)
+  std::vector<int2> host_tiles_;
+  std::vector<int> host_tile_row_;
+  DeviceBuffer<int2> tiles_part_[2];
+  int n_part_[2] = {0, 0};
+  int edge_rows_ = 0;
   CUtensorMap tm_x_[2];
   CUtensorMap tm_h_;
   CUtensorMap tm_h16_;

@@ -31,6 +31,9 @@ SIGNATURES = {
     "fpie_b200_grid_step": [c_void_p, c_int, u8p, f32p],
     "fpie_b200_grid_step_into": [c_void_p, c_int, u8p, c_i64, f32p],
     "fpie_b200_grid_set_formulation": [c_void_p, c_int],
+    "fpie_b200_grid_set_edge_rows": [c_void_p, c_int],
+    "fpie_b200_grid_pass_async": [c_void_p, c_int, c_int],
+    "fpie_b200_grid_flip": [c_void_p],
     "fpie_b200_grid_solve": [c_void_p, c_int, c_int, ctypes.c_float, f32p, intp],
     "fpie_b200_grid_state": [c_void_p, f32p],
     "fpie_b200_grid_sweeps_async": [c_void_p, c_int],

@@ -102,12 +102,15 @@ class BandGridSolver:
     never ends in a short pass.
     """
 
-    def __init__(self, core, dist, group=None, halo: int = 24):
+    def __init__(self, core, dist, group=None, halo: int = 24, overlap: bool = True):
         self.core, self.dist, self.group = core, dist, group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.halo = int(halo)
         self.plan: BandPlan | None = None
+        self.overlap = bool(overlap)
+        self._split = False  # passes are split into edge / interior tiles and the exchange overlaps the interior
+        self._pending = None  # event of the exchange in flight
 
     # -- reference interface -------------------------------------------------
     def reset(self, N, mask, tgt, grad) -> None:
@@ -118,11 +121,13 @@ class BandGridSolver:
         p = self.plan
         if p.band_hi == p.band_lo:
             self._empty = True
+            self._split = False
             return
         self._empty = False
         sl = slice(p.slab_lo, p.slab_hi)
         self.core.reset(int(p.slab_rows * mask.shape[1]), np.ascontiguousarray(mask[sl]), tgt[sl], grad[sl])
         self.core.set_row_window(*p.local_band)
+        self._plan_overlap()
 
     def reset_slab(self, n_rows: int, src_slab, mask_slab, tgt_slab, gradient: str) -> BandPlan:
         """Each rank passes only its own slab of the uint8 images (rows
@@ -135,7 +140,20 @@ class BandGridSolver:
                 raise ValueError(f"rank {self.rank}: slab has {src_slab.shape[0]} rows, plan needs {p.slab_rows}")
             self.core.reset_slab(src_slab, mask_slab, tgt_slab, gradient)
             self.core.set_row_window(*p.local_band)
+        self._plan_overlap()
         return p
+
+    def _plan_overlap(self) -> None:
+        """Split every pass into edge and interior tiles when the core can (CUDA) and there is a
+        neighbour: the exchange then runs on a second stream beside the interior of a pass."""
+        p = self.plan
+        self._pending = None
+        self._split = (self.overlap and not self._empty and (p.up is not None or p.down is not None)
+                       and hasattr(self.core, "pass_async"))
+        if self._split:
+            # edge tiles = those that write the rows we send (2 * halo from the slab edge) or read the halo
+            # rows we receive (their load region reaches block_k rows beyond what they store)
+            self.core.set_edge_rows(2 * self.halo + self.core.block_k)
 
     def sync(self) -> None:
         self.dist.barrier(self.group)
@@ -145,10 +163,61 @@ class BandGridSolver:
         left = int(iteration)
         while left > 0:
             s = min(self.halo, left)
-            if not self._empty:
-                self.core.sweeps_async(s)
-            self.exchange()
+            if self._split:
+                self._interval_overlapped(s)
+            else:
+                if not self._empty:
+                    self.core.sweeps_async(s)
+                self.exchange()
             left -= s
+        self._wait_exchange()
+
+    def _interval_overlapped(self, s: int) -> None:
+        """``s <= halo`` sweeps as passes of ``block_k``.  The LAST pass runs its edge tiles first and
+        hands the finished band-edge rows to the exchange while its interior tiles are still being
+        swept; the FIRST pass of the next interval sweeps its interior before it needs the received
+        halo rows.  Same arithmetic, same bits -- only the order of the tiles within a pass changes."""
+        core = self.core
+        k = core.block_k
+        sizes = [min(k, s - i) for i in range(0, s, k)]
+        for idx, ns in enumerate(sizes):
+            first, last = idx == 0, idx == len(sizes) - 1
+            if first and last:
+                self._wait_exchange()
+                core.pass_async(ns, core.EDGE)
+                self._start_exchange()
+                core.pass_async(ns, core.INTERIOR)
+            elif first:
+                core.pass_async(ns, core.INTERIOR)
+                self._wait_exchange()
+                core.pass_async(ns, core.EDGE)
+            elif last:
+                core.pass_async(ns, core.EDGE)
+                self._start_exchange()
+                core.pass_async(ns, core.INTERIOR)
+            else:
+                core.pass_async(ns, core.EDGE)
+                core.pass_async(ns, core.INTERIOR)
+            core.flip()
+
+    def _start_exchange(self) -> None:
+        """Enqueue the halo exchange on the communication stream, ordered after the edge tiles of the
+        pass just enqueued; it moves rows of the buffer that pass writes (current after ``flip``)."""
+        import torch
+
+        core = self.core
+        done = torch.cuda.Event()
+        done.record(core.compute_stream)
+        with torch.cuda.stream(core.comm_stream):
+            core.comm_stream.wait_event(done)
+            self.exchange(which=core.next_buffer())
+            self._pending = torch.cuda.Event()
+            self._pending.record(core.comm_stream)
+
+    def _wait_exchange(self) -> None:
+        if self._pending is not None:
+            self.core.compute_stream.wait_event(self._pending)
+            self._pending = None
 
     def step(self, iteration: int):
         """Returns ``(uint8 image of this rank's band [rows, m, 3], err[3])``; ``err``
@@ -172,9 +241,11 @@ class BandGridSolver:
         return self.core.state()[lo:hi]
 
     # -- halo exchange ---------------------------------------------------------
-    def exchange(self) -> None:
-        """Send the band's edge rows to the neighbours, receive their edge rows into the halo rows."""
+    def exchange(self, which=None) -> None:
+        """Send the band's edge rows to the neighbours, receive their edge rows into the halo rows
+        (``which``: state buffer to operate on, default the current one)."""
         p = self.plan
+        view = self.core.rows_view if which is None else (lambda lo, hi: self.core.rows_view(lo, hi, which))
         if self._empty or (p.up is None and p.down is None):
             return
         dist = self.dist
@@ -182,12 +253,12 @@ class BandGridSolver:
         ops = []
         if p.up is not None:
             h = lo  # halo rows actually held above the band (== self.halo away from the top edge)
-            for send, recv in zip(self.core.rows_view(lo, lo + h), self.core.rows_view(0, h)):
+            for send, recv in zip(view(lo, lo + h), view(0, h)):
                 ops.append(dist.P2POp(dist.isend, send, p.up, self.group))
                 ops.append(dist.P2POp(dist.irecv, recv, p.up, self.group))
         if p.down is not None:
             h = p.slab_rows - hi
-            for send, recv in zip(self.core.rows_view(hi - h, hi), self.core.rows_view(hi, hi + h)):
+            for send, recv in zip(view(hi - h, hi), view(hi, hi + h)):
                 ops.append(dist.P2POp(dist.isend, send, p.down, self.group))
                 ops.append(dist.P2POp(dist.irecv, recv, p.down, self.group))
         for req in dist.batch_isend_irecv(ops):
@@ -328,6 +399,11 @@ class CudaBandCore:
         self.solver = solver
         self.torch_device = torch.device("cuda", solver.device)
         self._views = {}
+        # the solver enqueues on the torch stream that was current when it was built
+        h = solver.stream_handle
+        self.compute_stream = (torch.cuda.ExternalStream(h, device=self.torch_device) if h
+                               else torch.cuda.default_stream(self.torch_device))
+        self.comm_stream = torch.cuda.Stream(self.torch_device)
 
     def reset(self, N, mask, tgt, grad):
         self.solver.reset(N, mask, tgt, grad)
@@ -369,8 +445,27 @@ class CudaBandCore:
             self._views[which] = planes
         return self._views[which]
 
-    def rows_view(self, lo: int, hi: int):
-        return [plane[lo:hi] for plane in self._planes(self.solver.current_buffer())]
+    def rows_view(self, lo: int, hi: int, which: int | None = None):
+        return [plane[lo:hi] for plane in self._planes(self.solver.current_buffer() if which is None else which)]
+
+    # -- split passes: halo exchange beside the interior of a pass --------------
+    EDGE, INTERIOR = 0, 1
+
+    @property
+    def block_k(self) -> int:
+        return self.solver.info()["block_k"]
+
+    def set_edge_rows(self, rows: int):
+        self.solver.set_edge_rows(rows)
+
+    def pass_async(self, nsweeps: int, part: int):
+        self.solver.pass_async(nsweeps, part)
+
+    def flip(self):
+        self.solver.flip()
+
+    def next_buffer(self) -> int:
+        return self.solver.current_buffer() ^ 1
 
 
 def init_process_group_from_env(backend: str | None = None):

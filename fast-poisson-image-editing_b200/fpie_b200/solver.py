@@ -88,6 +88,7 @@ class GridSolver(_Handle):
         self.device = default_device() if device is None else int(device)
         self.shape = None
         stream = _lib.current_stream_handle(self.device)
+        self.stream_handle = stream  # the torch stream that was current at construction
         _lib.check(self._lib.fpie_b200_grid_create(self.device, ctypes.c_void_p(stream), int(block_k), int(variant),
                                                    ctypes.byref(self._h)))
 
@@ -134,6 +135,21 @@ class GridSolver(_Handle):
         return img, err
 
     # -- extras ---------------------------------------------------------------
+    EDGE, INTERIOR = 0, 1
+
+    def set_edge_rows(self, rows: int) -> None:
+        """Split the tile list: tiles storing any of the first / last ``rows`` grid rows are the EDGE
+        part, the others the INTERIOR part (for ``pass_async``)."""
+        _lib.check(self._lib.fpie_b200_grid_set_edge_rows(self.handle, int(rows)))
+
+    def pass_async(self, nsweeps: int, part: int) -> None:
+        """One pass (``1..block_k`` sweeps) over one part of the tile list, no buffer flip."""
+        _lib.check(self._lib.fpie_b200_grid_pass_async(self.handle, int(nsweeps), int(part)))
+
+    def flip(self) -> None:
+        """Make the output of the pass just enqueued (both parts) the current state."""
+        _lib.check(self._lib.fpie_b200_grid_flip(self.handle))
+
     def set_formulation(self, equ: bool) -> None:
         """Image-level resets that follow build the EquSolver's system on the grid
         (``equ=True``: X / B of process.py:227-266, zero outside the mask) instead of

@@ -158,6 +158,19 @@ int fpie_b200_grid_band_current(fpie_b200_grid *g, int *which_buffer);
  * [row_lo, row_hi) -- a band counts only its own rows, not its halo. */
 int fpie_b200_grid_set_row_window(fpie_b200_grid *g, int row_lo, int row_hi);
 
+/* Split passes, so that the halo exchange of a band overlaps the bulk of a pass: after
+ * set_edge_rows(rows) the tiles whose stored rows intersect the first / last `rows` grid rows are the
+ * EDGE part (0) of the tile list, all others the INTERIOR part (1).  pass_async runs one pass
+ * (1..block_k sweeps) over one part on the solver's stream WITHOUT flipping the state buffers; after
+ * both parts of a pass have been enqueued (in either order) flip() makes its output the current state.
+ * The reference's MPI solver has no such overlap: it exchanges between sweeps, blocking
+ * (fpie/core/mpi/grid.cc:118-135). */
+#define FPIE_B200_PART_EDGE 0
+#define FPIE_B200_PART_INTERIOR 1
+int fpie_b200_grid_set_edge_rows(fpie_b200_grid *g, int rows);
+int fpie_b200_grid_pass_async(fpie_b200_grid *g, int nsweeps, int part);
+int fpie_b200_grid_flip(fpie_b200_grid *g);
+
 /* Formulation built by the image-level resets (reset_from_images / reset_slab) that follow:
  * 0 (default) = GridSolver's (unmasked pixels hold the target, fpie/process.py:354-378);
  * 1 = EquSolver's, laid out on the grid: unknowns carry X = target and B = grad + the targets of

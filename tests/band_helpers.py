@@ -114,7 +114,10 @@ class ThreadDist:
         me = self.local.rank
         for op in ops:
             if op.op == "isend":
-                self.q[(me, op.peer)].put(op.tensor.clone())
+                sent = op.tensor.clone()
+                if sent.is_cuda:  # the receiver copies on ITS stream: the clone must have completed
+                    torch.cuda.current_stream(sent.device).synchronize()
+                self.q[(me, op.peer)].put(sent)
         for op in ops:
             if op.op == "irecv":
                 op.tensor.copy_(self.q[(op.peer, me)].get(timeout=120))
