@@ -732,6 +732,9 @@ void GridSolver::auto_configure(int n, int m) {
     v = 36, k = 8;
   else
     v = 24, k = 8;
+  // very wide, flat grids: a tile much taller than the grid sweeps mostly padding
+  if (v != 12 && n <= 36) v = 12;
+  else if (v == 24 && n <= 72) v = 36;
   if (!auto_k_) k = block_k_;  // the caller's depth wins; take the tallest tile if the small one cannot hold it
   if (shape_for(v).tile_h() <= 2 * k) v = 24;
   configure(v, k);

@@ -298,3 +298,66 @@ def test_full_size_temporal_blocking_invariance():
             np.testing.assert_array_equal(out, ref[1])
             np.testing.assert_allclose(err, ref[2], rtol=1e-6)
         proc.core.close()
+
+
+@pytest.mark.parametrize("variant,block_k,edge", [(0, 0, 40), (24, 8, 1), (36, 16, 100), (12, 4, 17), (20, 8, 30), (2, 8, 64)])
+def test_split_passes_give_the_same_bits(variant, block_k, edge):
+    """set_edge_rows / pass_async / flip (the row-band solver's overlap schedule): running a pass as
+    edge tiles + interior tiles, in either order, is the same pass."""
+    mask, tgt, grad = _random_grid(523, 300, seed=31)
+    s = _solver(variant, block_k)
+    s.reset(mask.size, mask, tgt, grad)
+    k = s.info()["block_k"]
+    with pytest.raises(RuntimeError, match="set_edge_rows"):
+        s.pass_async(1, s.EDGE)
+    s.set_edge_rows(edge)
+    done = 0
+    for i, ns in enumerate([k, k, max(k // 2, 1), 1, k]):
+        order = (s.EDGE, s.INTERIOR) if i % 2 == 0 else (s.INTERIOR, s.EDGE)
+        for part in order:
+            s.pass_async(ns, part)
+        s.flip()
+        done += ns
+    s.sweeps_async(7)  # whole passes keep working afterwards
+    done += 7
+    want = c_oracle.grid_sweeps(mask, tgt, grad, done)
+    np.testing.assert_array_equal(s.state(), want)
+    with pytest.raises(RuntimeError, match="1..block_k"):
+        s.pass_async(k + 1, s.EDGE)
+    with pytest.raises(RuntimeError, match="part"):
+        s.pass_async(1, 2)
+    # a new reset drops the partition
+    s.reset(mask.size, mask, tgt, grad)
+    with pytest.raises(RuntimeError, match="set_edge_rows"):
+        s.pass_async(1, s.INTERIOR)
+
+
+def test_equ_formulation_on_the_grid_matches_the_equ_oracle():
+    """set_formulation(True) + reset_from_images: the GridSolver runs the EquSolver's arithmetic
+    (X on the mask, 0 elsewhere, gradient B) and reproduces the EquSolver's unknowns bit for bit."""
+    import fpie_b200
+    from fpie_b200 import synth
+
+    for kind, mode in (("star", "max"), ("holes", "avg"), ("ring", "src")):
+        src, mask, tgt = synth.make_problem(kind, 301, 277, seed=13)
+        s = fpie_b200.GridSolver(8, 8)
+        s.set_formulation(True)
+        s.reset_from_images(src, mask, tgt, (0, 0), (0, 0), mode)
+        img, err = s.step(33)
+        n, A, X, B, index = np_oracle.equ_system(src, mask, tgt, (0, 0), (0, 0), mode)
+        want = c_oracle.equ_sweeps(A, X, B, 33)
+        m_full, (x0, x1, y0, y1) = np_oracle.canonical_mask(mask)
+        crop = m_full[x0:x1, y0:y1]
+        ids = np_oracle.partition_rowmajor(crop)
+        state = s.state()
+        on = crop > 0
+        np.testing.assert_array_equal(state[on], want[ids[on]])
+        assert not state[~on].any()
+        np.testing.assert_array_equal(img[on], c_oracle.clip_u8(want)[ids[on]])
+        np.testing.assert_allclose(err, c_oracle.equ_residual(A, want, B)[1], rtol=ERR_RTOL)
+        s.set_formulation(False)  # and back: the GridSolver's own system again
+        s.reset_from_images(src, mask, tgt, (0, 0), (0, 0), mode)
+        s.step(5)
+        g = np_oracle.GridOracle(mode)
+        g.reset(src, mask, tgt, (0, 0), (0, 0))
+        np.testing.assert_array_equal(s.state(), c_oracle.grid_sweeps(g.mask, g.t, g.g, 5))
