@@ -717,6 +717,26 @@ void GridSolver::configure(int variant, int block_k) {
   FPIE_REQUIRE(shape_.tile_h() > 2 * block_k_, "block_k too deep for the tile height");
 }
 
+// Candidate (tile shape, depth) pairs of the automatic configuration and the cost model that ranks them
+// on grids of up to 12 Mpx, where the number of waves a pass needs on 148 SMs decides (a pass over 543
+// tiles on 296 CTA slots costs two full waves).  Per-wave time of one pass = a + b * k microseconds, fitted
+// to tools/tune_grid.py runs at 512^2 .. 3072^2 (profiles/r01_tune_small_grids.json; the picks lose 0-6 % against
+// the best measured configuration of each size and gain up to 18 % over a size-only rule); `launch` = per-pass launch cost.
+struct TileChoice {
+  int variant, k, occ;
+  double a, b;
+};
+static const TileChoice kTileChoices[] = {
+    {12, 6, 2, 1.68, 0.427},  {12, 8, 2, 1.68, 0.427},  {12, 10, 2, 1.68, 0.427}, {12, 12, 2, 1.68, 0.427},
+    {12, 16, 2, 1.68, 0.427}, {36, 6, 2, 2.22, 0.531},  {36, 8, 2, 2.22, 0.531},  {36, 10, 2, 2.22, 0.531},
+    {36, 12, 2, 2.22, 0.531}, {36, 16, 2, 2.22, 0.531}, {24, 8, 1, 2.70, 0.551},  {24, 10, 1, 2.70, 0.551},
+    {24, 12, 1, 2.70, 0.551}, {24, 16, 1, 2.70, 0.551},
+};
+constexpr double kLaunchUs = 4.0;
+// the last, partial wave of a two-CTAs-per-SM shape is cheaper when it leaves one CTA per SM
+constexpr double kLoneCtaWave = 0.85;
+constexpr long long kModelMaxPixels = 12000000;
+
 // Automatic configuration (measured on B200, tools/tune_grid.py, profiles/r01_tune_variants_k.json): small
 // grids cannot fill 148 SMs with 168-row tiles and pay the per-launch latency once per pass, so they get
 // 64-row tiles on two CTAs per SM and deeper temporal blocking; mid-size grids 84-row tiles (21 rows per
@@ -756,11 +776,13 @@ void GridSolver::layout(int n, int m) {
   long long need_cols = (long long)tiles_x * step_x + halo_x_ + 4;
   int need_rows = tiles_y * step_y + block_k_ + 1;
   if (auto_tune_ && auto_k_) {
-    // the depth may still be raised to 12 once the unknown count is known (after_state_loaded): make
-    // the padded planes large enough for that tiling too
-    const int sx12 = TILE_W - 2 * 12, sy12 = shape_.tile_h() - 2 * 12;
-    need_cols = std::max(need_cols, (long long)ceil_div(m, sx12) * sx12 + 12 + 4);
-    need_rows = std::max(need_rows, (int)ceil_div(n, sy12) * sy12 + 12 + 1);
+    // shape and depth may still change once the mask is on the device (choose_by_model, the k = 12 rule
+    // of after_state_loaded): make the padded planes large enough for every tiling that can be picked
+    for (const TileChoice &c : kTileChoices) {
+      const int hx = (int)round_up(c.k, 4), sx = TILE_W - 2 * hx, sy = shape_for(c.variant).tile_h() - 2 * c.k;
+      need_cols = std::max(need_cols, (long long)ceil_div(m, sx) * sx + hx + 4);
+      need_rows = std::max(need_rows, (int)ceil_div(n, sy) * sy + c.k + 1);
+    }
   }
   g.pitch = (int)round_up(g.padc + need_cols, 128);
   g.rows = g.padr + need_rows;
@@ -926,14 +948,60 @@ void GridSolver::after_state_loaded() {
   // large and (almost) fully masked grids: every tile is a select-free full tile, and the per-tile cost
   // amortises better over 12 sweeps than over 8 (measured 894 -> 934 Gupd/s at 4096^2, 2011 -> 2114 on two
   // 16384 x 32768 bands); masks with a long boundary prefer 8 (fewer partially filled boundary tiles)
-  if (auto_k_ && auto_tune_ && (long long)geom_.n * geom_.m > 6000000 &&
+  if (auto_k_ && auto_tune_ && (long long)geom_.n * geom_.m > kModelMaxPixels &&
       (double)stats_.unknowns >= 0.9 * (double)geom_.n * (double)geom_.m)
     configure(variant_, 12);
+  if (auto_k_ && auto_tune_ && batch_.batch == 0 && stats_.unknowns > 0 &&
+      (long long)geom_.n * geom_.m <= kModelMaxPixels)
+    choose_by_model();
   make_tensor_maps();
   build_tiles();
   CUDA_CHECK(cudaStreamSynchronize(stream_));
   cur_ = 0;
   ready_ = true;
+}
+
+// Small and mid-size grids: count the active tiles of every candidate tiling on the device and take the
+// one with the lowest modelled time per sweep, (waves x per-wave time + launch) / k.
+void GridSolver::choose_by_model() {
+  const PlaneGeom &g = geom_;
+  constexpr int NC = (int)(sizeof(kTileChoices) / sizeof(kTileChoices[0]));
+  size_t offset[NC + 1] = {0};
+  int tiles_x[NC], tile_h[NC], hx[NC];
+  for (int i = 0; i < NC; ++i) {
+    const TileChoice &c = kTileChoices[i];
+    tile_h[i] = shape_for(c.variant).tile_h();
+    hx[i] = (int)round_up(c.k, 4);
+    tiles_x[i] = (int)ceil_div(g.m, TILE_W - 2 * hx[i]);
+    offset[i + 1] = offset[i] + (size_t)tiles_x[i] * ceil_div(g.n, tile_h[i] - 2 * c.k);
+  }
+  tile_flags_.resize(offset[NC]);
+  for (int i = 0; i < NC; ++i) {
+    const TileChoice &c = kTileChoices[i];
+    const int n_i = (int)(offset[i + 1] - offset[i]);
+    classify_tiles_kernel<<<n_i, 256, 0, stream_>>>(g, bits_.ptr, tiles_x[i], tile_h[i], tile_h[i] - 2 * c.k,
+                                                    TILE_W - 2 * hx[i], c.k, hx[i], tile_flags_.ptr + offset[i]);
+  }
+  CUDA_CHECK(cudaGetLastError());
+  stats_.launches += NC;
+  std::vector<uint32_t> flags(offset[NC]);
+  CUDA_CHECK(cudaMemcpyAsync(flags.data(), tile_flags_.ptr, flags.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                             stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  int best = -1;
+  double best_cost = 0.0;
+  for (int i = 0; i < NC; ++i) {
+    const TileChoice &c = kTileChoices[i];
+    long long active = 0;
+    for (size_t t = offset[i]; t < offset[i + 1]; ++t) active += flags[t] & 1u;
+    const long long slots = (long long)sm_count_ * c.occ, items = 3 * active;
+    const long long full = items / slots, rest = items - full * slots;
+    double waves = (double)full;
+    if (rest > 0) waves += (c.occ == 2 && rest <= sm_count_) ? kLoneCtaWave : 1.0;
+    const double cost = (waves * (c.a + c.b * c.k) + kLaunchUs) / c.k;
+    if (best < 0 || cost < best_cost) best = i, best_cost = cost;
+  }
+  configure(kTileChoices[best].variant, kTileChoices[best].k);
 }
 
 void GridSolver::build_tiles() {

@@ -89,6 +89,7 @@ class GridSolver {
   void make_tensor_maps();
   void configure(int variant, int block_k);
   void auto_configure(int n, int m);
+  void choose_by_model();
   void build_from_upload();
   static TileShape shape_for(int variant);
 
