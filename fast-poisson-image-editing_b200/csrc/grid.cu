@@ -13,6 +13,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "grid_solver.cuh"
@@ -702,10 +703,14 @@ GridSolver::GridSolver(int device, cudaStream_t stream, int block_k, int variant
   configure(variant_ == 0 ? 39 : variant_, block_k);
   err_.resize(4);
   CUDA_CHECK(cudaMallocHost(&host_err_, 4 * sizeof(double)));
+  const char *no_graph = getenv("FPIE_B200_NO_GRAPH");
+  graph_off_ = no_graph && no_graph[0] && no_graph[0] != '0';
 }
 
 GridSolver::~GridSolver() {
   cudaSetDevice(device_);
+  drop_graphs();
+  if (cap_stream_) cudaStreamDestroy(cap_stream_);
   if (host_err_) cudaFreeHost(host_err_);
 }
 
@@ -1034,6 +1039,7 @@ void GridSolver::build_tiles() {
   }
   edge_rows_ = 0;
   n_part_[0] = n_part_[1] = 0;
+  drop_graphs();  // they hold the old tile list, tensor maps and tile shape
   stats_.active_tiles = active;
   stats_.total_tiles = ntiles;
   n_tile_entries_ = (int)list.size();
@@ -1245,17 +1251,64 @@ void GridSolver::sweeps_async(int iters) {
   a.halo_y = block_k_;
   a.halo_x = halo_x_;
   int left = iters;
+  auto one_pass = [&](SweepArgs &args, int &cur, int nsweeps) {
+    args.nsweeps = nsweeps;
+    args.xin = x_[cur].ptr;
+    args.xout = x_[cur ^ 1].ptr;
+    args.tm_x = &tm_x_[cur];
+    launch_variant(variant_, args);
+    cur ^= 1;
+  };
+  // long runs: replay a captured graph of kGraphPasses full passes (an even number, so the graph starts
+  // and ends on the same state buffer) -- the launch-bound inner loop of a step costs one graph launch
+  // per kGraphPasses kernels
+  if (!graph_off_ && left >= 2 * kGraphPasses * block_k_) {
+    if (!graph_warm_) {  // per-function attributes are set lazily at the first launch: not inside a capture
+      for (int i = 0; i < 2; ++i) one_pass(a, cur_, block_k_);
+      left -= 2 * block_k_;
+      stats_.launches += 2;
+      graph_warm_ = true;
+    }
+    if (!graph_[cur_]) {
+      if (!cap_stream_) CUDA_CHECK(cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking));
+      SweepArgs b = a;
+      b.stream = cap_stream_;  // (the solver's own stream may be the legacy default stream, which cannot capture)
+      int c = cur_;
+      CUDA_CHECK(cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal));
+      cudaGraph_t captured = nullptr;
+      try {
+        for (int i = 0; i < kGraphPasses; ++i) one_pass(b, c, block_k_);
+      } catch (...) {
+        cudaStreamEndCapture(cap_stream_, &captured);
+        if (captured) cudaGraphDestroy(captured);
+        throw;
+      }
+      CUDA_CHECK(cudaStreamEndCapture(cap_stream_, &captured));
+      const cudaError_t rc = cudaGraphInstantiate(&graph_[cur_], captured, 0);
+      cudaGraphDestroy(captured);
+      CUDA_CHECK(rc);
+    }
+    while (left >= kGraphPasses * block_k_) {
+      CUDA_CHECK(cudaGraphLaunch(graph_[cur_], stream_));
+      left -= kGraphPasses * block_k_;
+      stats_.launches += kGraphPasses;
+    }
+  }
   while (left > 0) {
-    a.nsweeps = std::min(left, block_k_);
-    a.xin = x_[cur_].ptr;
-    a.xout = x_[cur_ ^ 1].ptr;
-    a.tm_x = &tm_x_[cur_];
-    launch_variant(variant_, a);
-    cur_ ^= 1;
-    left -= a.nsweeps;
+    const int ns = std::min(left, block_k_);
+    one_pass(a, cur_, ns);
+    left -= ns;
     stats_.launches += 1;
   }
   CUDA_CHECK(cudaGetLastError());
+}
+
+void GridSolver::drop_graphs() {
+  for (auto &gx : graph_) {
+    if (gx) cudaGraphExecDestroy(gx);
+    gx = nullptr;
+  }
+  graph_warm_ = false;
 }
 
 // ---- split passes (row-band sharding: overlap the halo exchange with the interior of a pass) ----------

@@ -90,6 +90,7 @@ class GridSolver {
   void configure(int variant, int block_k);
   void auto_configure(int n, int m);
   void choose_by_model();
+  void drop_graphs();
   void build_from_upload();
   static TileShape shape_for(int variant);
 
@@ -124,6 +125,11 @@ class GridSolver {
   DeviceBuffer<double> err_;  // [3] residual sums + [1] unknown count (as double)
   DeviceBuffer<int2> tiles_;
   DeviceBuffer<uint32_t> tile_flags_;
+  // CUDA graph of kGraphPasses full passes per starting buffer, replayed by long sweeps_async calls
+  static constexpr int kGraphPasses = 16;
+  cudaStream_t cap_stream_ = nullptr;
+  cudaGraphExec_t graph_[2] = {nullptr, nullptr};
+  bool graph_off_ = false, graph_warm_ = false;
   // edge / interior partition of the tile list (set_edge_rows)
   std::vector<int2> host_tiles_;
   std::vector<int> host_tile_row_;

@@ -361,3 +361,25 @@ def test_equ_formulation_on_the_grid_matches_the_equ_oracle():
         g = np_oracle.GridOracle(mode)
         g.reset(src, mask, tgt, (0, 0), (0, 0))
         np.testing.assert_array_equal(s.state(), c_oracle.grid_sweeps(g.mask, g.t, g.g, 5))
+
+
+@pytest.mark.parametrize("variant,block_k", [(0, 0), (24, 3), (36, 2), (12, 1), (20, 2), (2, 2), (124, 4)])
+def test_long_runs_replay_a_cuda_graph(variant, block_k):
+    """step(iters) with iters >= 32 passes replays a captured graph of 16 passes: same bits, from either
+    state buffer, across resets (which drop the graph), and mixed with short steps."""
+    mask, tgt, grad = _random_grid(210, 260, seed=77)
+    s = _solver(variant, block_k)
+    s.reset(mask.size, mask, tgt, grad)
+    k = s.info()["block_k"]
+    total = 0
+    for it in (32 * k + 5, k, 33 * k, 3, 40 * k + 1):  # the odd pass counts flip the starting buffer
+        s.step(it)
+        total += it
+        np.testing.assert_array_equal(s.state(), c_oracle.grid_sweeps(mask, tgt, grad, total))
+    launches = s.info()["launches"]
+    assert launches >= total // k
+    mask2, tgt2, grad2 = _random_grid(150, 333, seed=78)
+    s.reset(mask2.size, mask2, tgt2, grad2)
+    k2 = s.info()["block_k"]
+    s.step(35 * k2)
+    np.testing.assert_array_equal(s.state(), c_oracle.grid_sweeps(mask2, tgt2, grad2, 35 * k2))
