@@ -284,12 +284,14 @@ def test_full_size_temporal_blocking_invariance():
 
     src, mask, tgt = synth.make_problem("circle", 4096, 4096, seed=0)
     ref = None
-    for variant, k in ((1, 0), (0, 8), (0, 16), (2, 4), (4, 8), (5, 12), (6, 5), (8, 8), (10, 6), (20, 8), (20, 12), (22, 6)):
+    # (272 sweeps: long enough for the default configuration to replay its CUDA graph of 16 passes)
+    for variant, k in ((1, 0), (0, 0), (0, 8), (0, 16), (24, 12), (36, 8), (39, 8), (18, 8), (2, 4), (4, 8), (5, 12), (6, 5),
+                       (8, 8), (10, 6), (20, 8), (20, 12), (22, 6)):
         proc = fpie_b200.GridProcessor("max", "b200")
         proc.core.close()
         proc.core = fpie_b200.GridSolver(8, 8, block_k=k, variant=variant)
         proc.reset(src, mask, tgt, (0, 0), (0, 0))
-        out, err = proc.step(100)
+        out, err = proc.step(272)
         digest = (out.astype(np.uint64).sum(), proc.core.state().view(np.uint32).astype(np.uint64).sum())
         if ref is None:
             ref = (digest, out.copy(), err.copy())
