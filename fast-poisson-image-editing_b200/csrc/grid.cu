@@ -340,7 +340,7 @@ template <int R, int NW, int OCC, bool H16>
 __global__ void __launch_bounds__(NW * 32, OCC)
 grid_sweepk_pipe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h,
                         const __grid_constant__ CUtensorMap tm_m, PlaneGeom g, float *__restrict__ xout,
-                        const int2 *__restrict__ tiles, int ntiles, int nsweeps, int halo_y, int halo_x) {
+                        const int2 *__restrict__ tiles, int ntiles, int nsweeps, int halo_y, int halo_x, int reverse) {
   constexpr int TH = R * NW;
   using L = PipeSmem<R, NW, H16>;
   constexpr int H16_W = L::H16_W;
@@ -373,8 +373,12 @@ grid_sweepk_pipe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
   int t = blockIdx.x;
   if (t >= ntiles) return;
   const int stride = gridDim.x;
-  int2 cur = tiles[t];  // (the tile list is not written by the sweep kernels: safe before the dependency wait)
-  int2 nxt = (t + stride < ntiles) ? tiles[t + stride] : cur;
+  // every other pass walks the tile list backwards: it starts on the tiles the previous pass wrote last,
+  // which are still in L2
+  if (reverse) tiles += ntiles - 1;
+  const int dir = reverse ? -1 : 1;
+  int2 cur = tiles[dir * t];  // (the tile list is not written by the sweep kernels: safe before the dependency wait)
+  int2 nxt = (t + stride < ntiles) ? tiles[dir * (t + stride)] : cur;
   // programmatic dependent launch: let the next pass get scheduled, then wait for the previous pass --
   // it wrote the state this pass reads and read the buffer this pass overwrites
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -384,7 +388,7 @@ grid_sweepk_pipe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
   uint32_t phase = 0, mphase = 0;
   for (; t < ntiles; t += stride) {
     // descriptor of the tile after next: consumed one full iteration from now
-    const int2 nxt2 = (t + 2 * stride < ntiles) ? tiles[t + 2 * stride] : nxt;
+    const int2 nxt2 = (t + 2 * stride < ntiles) ? tiles[dir * (t + 2 * stride)] : nxt;
     const TileRef td = unpack_tile(cur);
     const int pcol = td.pcol + 4 * lane;
     const long long base = (long long)td.plane * g.plane + (long long)(td.prow + w * R) * g.pitch + pcol;
@@ -703,6 +707,8 @@ GridSolver::GridSolver(int device, cudaStream_t stream, int block_k, int variant
   configure(variant_ == 0 ? 39 : variant_, block_k);
   err_.resize(4);
   CUDA_CHECK(cudaMallocHost(&host_err_, 4 * sizeof(double)));
+  const char *no_serp = getenv("FPIE_B200_NO_SERPENTINE");
+  serpentine_ = !(no_serp && no_serp[0] && no_serp[0] != '0');
   const char *no_graph = getenv("FPIE_B200_NO_GRAPH");
   graph_off_ = no_graph && no_graph[0] && no_graph[0] != '0';
 }
@@ -1064,6 +1070,7 @@ struct SweepArgs {
   const int2 *tiles;
   const CUtensorMap *tm_m;
   bool h16;
+  int reverse;  // walk the tile list backwards (alternate passes: L2 reuse of the previous pass's last tiles)
   int ntiles, nsweeps, halo_y, halo_x;
 };
 
@@ -1100,7 +1107,7 @@ void launch_pipe_h(const SweepArgs &a) {
   // (measured: a win once there is at least one tile per SM, a loss for grids of a few dozen tiles)
   cfg.numAttrs = (a.ntiles >= a.grid) ? 1 : 0;
   CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, *a.tm_x, *a.tm_h, *a.tm_m, a.g, a.xout, a.tiles, a.ntiles, a.nsweeps,
-                                a.halo_y, a.halo_x));
+                                a.halo_y, a.halo_x, a.reverse));
 }
 
 template <int R, int NW, int OCC>
@@ -1256,6 +1263,7 @@ void GridSolver::sweeps_async(int iters) {
     args.xin = x_[cur].ptr;
     args.xout = x_[cur ^ 1].ptr;
     args.tm_x = &tm_x_[cur];
+    args.reverse = (serpentine_ && cur) ? 1 : 0;
     launch_variant(variant_, args);
     cur ^= 1;
   };

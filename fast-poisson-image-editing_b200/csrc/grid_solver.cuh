@@ -130,6 +130,7 @@ class GridSolver {
   cudaStream_t cap_stream_ = nullptr;
   cudaGraphExec_t graph_[2] = {nullptr, nullptr};
   bool graph_off_ = false, graph_warm_ = false;
+  bool serpentine_ = true;  // alternate passes walk the tile list in opposite directions
   // edge / interior partition of the tile list (set_edge_rows)
   std::vector<int2> host_tiles_;
   std::vector<int> host_tile_row_;
