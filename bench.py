@@ -302,6 +302,8 @@ def run_single(args, work, name):
     # dominant kernel: the sweep kernel; algorithmic bytes per launch / mean launch duration
     per_update = GRID_BYTES_PER_UPDATE if is_grid else EQU_BYTES_PER_UPDATE
     k = info0.get("block_k", 1) if is_grid else 1
+    kernel_cfg = ({"tile": list(info0["tile"]), "rows_per_thread": info0["rows_per_thread"], "warps": info0["warps"],
+                   "ctas_per_sm": info0["ctas_per_sm"], "variant": info0["variant"]} if is_grid else None)
     sweep_launches = (iters + k - 1) // k
     launch_s = float(np.mean(sweep_ms)) * 1e-3 / sweep_launches
     sweeps_per_launch = iters / sweep_launches
@@ -391,6 +393,7 @@ def run_single(args, work, name):
             "n_vars": nvars,
             "sweeps_per_step": iters,
             "block_k": k,
+            "kernel": kernel_cfg,
             "tiles": [info0.get("active_tiles"), info0.get("total_tiles")] if is_grid else None,
             "l2": (f"working set {unknowns * per_update / 1e6:.0f} MB per sweep exceeds the 126 MB L2; no flush needed"
                    if unknowns * per_update > 2 * 126e6 else
@@ -526,7 +529,7 @@ def run_band(args, work, name):
                 "sweeps_per_step": iters,
                 "block_k": k,
                 "halo": halo,
-                "exchange": "overlapped with the interior tiles of a pass (second stream)" if solver._split
+                "exchange": "overlapped with the interior tiles of a pass (second stream)" if solver.exchange_overlaps
                 else "between passes",
                 "band_rows": plan.band_hi - plan.band_lo,
                 "l2": "per-GPU slab far exceeds the 126 MB L2; no flush needed",

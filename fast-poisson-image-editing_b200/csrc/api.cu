@@ -152,6 +152,10 @@ API int fpie_b200_grid_info(fpie_b200_grid *g, int64_t *unknowns, int64_t *launc
     if (total_tiles) *total_tiles = s.total_tiles;
   });
 }
+API int fpie_b200_grid_config(fpie_b200_grid *g, int *variant, int *rows_per_thread, int *warps, int *ctas_per_sm) {
+  NEED(g);
+  return guarded([&] { g->impl.config(variant, rows_per_thread, warps, ctas_per_sm); });
+}
 API int fpie_b200_grid_reset_from_images(fpie_b200_grid *g, const uint8_t *src, int sh, int sw, const uint8_t *mask,
                                          int mh, int mw, int mc, const uint8_t *tgt, int th, int tw, int h0, int w0,
                                          int h1, int w1, int grad_mode, int64_t *out_n, int32_t *out_box4) {

@@ -1213,6 +1213,14 @@ static void launch_variant(int variant, const SweepArgs &a) {
 
 }  // namespace
 
+void GridSolver::config(int *variant, int *rows, int *warps, int *occ) const {
+  const VariantInfo v = variant_info(variant_);
+  if (variant) *variant = variant_;
+  if (rows) *rows = v.rows;
+  if (warps) *warps = v.warps;
+  if (occ) *occ = v.occ;
+}
+
 TileShape GridSolver::shape_for(int variant) {
   const VariantInfo v = variant_info(variant);
   return {v.rows, v.warps};

@@ -78,6 +78,7 @@ class GridSolver {
   int device() const { return device_; }
   int block_k() const { return block_k_; }
   int current() const { return cur_; }
+  void config(int *variant, int *rows, int *warps, int *occ) const;
   const GridStats &stats() const { return stats_; }
   const PlaneGeom &geom() const { return geom_; }
 

@@ -30,6 +30,7 @@ SIGNATURES = {
     "fpie_b200_grid_reset": [c_void_p, c_int, c_int, i32p, c_i64, c_i64, f32p, f32p],
     "fpie_b200_grid_step": [c_void_p, c_int, u8p, f32p],
     "fpie_b200_grid_step_into": [c_void_p, c_int, u8p, c_i64, f32p],
+    "fpie_b200_grid_config": [c_void_p, intp, intp, intp, intp],
     "fpie_b200_grid_set_formulation": [c_void_p, c_int],
     "fpie_b200_grid_set_edge_rows": [c_void_p, c_int],
     "fpie_b200_grid_pass_async": [c_void_p, c_int, c_int],

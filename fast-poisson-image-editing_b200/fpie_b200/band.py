@@ -112,6 +112,11 @@ class BandGridSolver:
         self._split = False  # passes are split into edge / interior tiles and the exchange overlaps the interior
         self._pending = None  # event of the exchange in flight
 
+    @property
+    def exchange_overlaps(self) -> bool:
+        """True when passes are split and the halo exchange runs beside their interior tiles."""
+        return self._split
+
     # -- reference interface -------------------------------------------------
     def reset(self, N, mask, tgt, grad) -> None:
         """Every rank passes the same global arrays (what ``sync()`` leaves on each

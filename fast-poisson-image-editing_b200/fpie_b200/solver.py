@@ -268,8 +268,12 @@ class GridSolver(_Handle):
         k = ctypes.c_int()
         _lib.check(self._lib.fpie_b200_grid_info(self.handle, ctypes.byref(unk), ctypes.byref(launches),
                                                  ctypes.byref(k), ctypes.byref(act), ctypes.byref(tot)))
+        v, rows, warps, occ = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _lib.check(self._lib.fpie_b200_grid_config(self.handle, ctypes.byref(v), ctypes.byref(rows), ctypes.byref(warps),
+                                                   ctypes.byref(occ)))
         return dict(unknowns=unk.value, launches=launches.value, block_k=k.value, active_tiles=act.value,
-                    total_tiles=tot.value)
+                    total_tiles=tot.value, variant=v.value, tile=(rows.value * warps.value, 128),
+                    rows_per_thread=rows.value, warps=warps.value, ctas_per_sm=occ.value)
 
     def set_row_window(self, lo: int, hi: int) -> None:
         _lib.check(self._lib.fpie_b200_grid_set_row_window(self.handle, int(lo), int(hi)))

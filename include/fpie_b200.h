@@ -113,6 +113,10 @@ int fpie_b200_grid_fetch(fpie_b200_grid *g, uint8_t *out_img, float *out_err3);
 int fpie_b200_grid_info(fpie_b200_grid *g, int64_t *unknowns, int64_t *launches, int *block_k,
                         int64_t *active_tiles, int64_t *total_tiles);
 
+/* The kernel configuration in use (chosen at reset when `variant` / `block_k` were 0): the variant
+ * number, the register tile (rows per thread x warps per CTA, 128 columns) and CTAs per SM. */
+int fpie_b200_grid_config(fpie_b200_grid *g, int *variant, int *rows_per_thread, int *warps, int *ctas_per_sm);
+
 /* Fused Processor-level reset (GridProcessor.reset, fpie/process.py:321-386)
  * executed on the device from uint8 images: mask threshold / frame clear /
  * bounding box, crop, mixed gradient, state upload.
