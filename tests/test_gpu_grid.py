@@ -385,3 +385,18 @@ def test_long_runs_replay_a_cuda_graph(variant, block_k):
     k2 = s.info()["block_k"]
     s.step(35 * k2)
     np.testing.assert_array_equal(s.state(), c_oracle.grid_sweeps(mask2, tgt2, grad2, 35 * k2))
+
+
+def test_info_reports_the_kernel_configuration():
+    """Automatic configuration: the shape follows the grid (small tiles on two CTAs per SM for small
+    grids, the 8-warp x 21-row tile for large ones); explicit variants are reported as given."""
+    mask, tgt, grad = _random_grid(120, 150, seed=3)
+    s = _solver()
+    s.reset(mask.size, mask, tgt, grad)
+    info = s.info()
+    assert info["tile"][1] == 128 and info["tile"][0] == info["rows_per_thread"] * info["warps"]
+    assert info["ctas_per_sm"] == 2 and info["tile"][0] <= 84 and 1 <= info["block_k"] <= 16
+    s = _solver(24, 8)
+    s.reset(mask.size, mask, tgt, grad)
+    info = s.info()
+    assert (info["variant"], info["rows_per_thread"], info["warps"], info["ctas_per_sm"], info["block_k"]) == (24, 21, 8, 1, 8)
