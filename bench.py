@@ -317,12 +317,17 @@ def run_single(args, work, name):
         "peak": peak,
         "unit": "GB/s",
         "frac": achieved / peak,
-        "traffic": profiled_traffic(kernel),
+        # (the ncu capture is of config 2 for the grid kernel and of config 3 for the gather kernel)
+        "traffic": profiled_traffic(kernel) if (name == ("cfg2" if is_grid else "cfg3") and not args.size) else None,
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": per_update * unknowns * sweeps_per_launch,
         "launch_us": launch_s * 1e6,
         "note": "effective (algorithmic) bandwidth; with k sweeps fused per launch real DRAM traffic is ~1/k of it",
     }
+    if roofline["traffic"]:
+        # the profiled DRAM bytes of one launch of exactly this workload over the live launch time: how busy HBM is
+        roofline["dram_achieved"] = roofline["traffic"] / launch_s / 1e9
+        roofline["dram_frac"] = roofline["dram_achieved"] / peak
 
     if is_grid:
         # second view of the same kernel: with k sweeps per pass the binding resource is instruction issue /
@@ -394,6 +399,7 @@ def run_single(args, work, name):
             "sweeps_per_step": iters,
             "block_k": k,
             "kernel": kernel_cfg,
+            "gpx_per_s": (nvars * iters / (ms_per_step * 1e-3) / 1e9) if is_grid and not is_batch else None,
             "tiles": [info0.get("active_tiles"), info0.get("total_tiles")] if is_grid else None,
             "l2": (f"working set {unknowns * per_update / 1e6:.0f} MB per sweep exceeds the 126 MB L2; no flush needed"
                    if unknowns * per_update > 2 * 126e6 else
@@ -537,7 +543,7 @@ def run_band(args, work, name):
             },
             "roofline": {
                 "bound": "hbm", "kernel": "grid_sweepk_pipe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": profiled_traffic("grid_sweepk_pipe_kernel"),
+                "frac": achieved / peak, "traffic": None,  # (the ncu capture is of config 2 on one GPU)
                 "peak_source": peak_src,
                 "note": "per-GPU effective bandwidth (36 B x unknowns of one band x sweeps / step time, halo "
                         "exchange and epilogue included)",
