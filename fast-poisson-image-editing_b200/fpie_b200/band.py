@@ -20,6 +20,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
+import contextlib
+
 import numpy as np
 
 
@@ -110,7 +112,6 @@ class BandGridSolver:
         self.plan: BandPlan | None = None
         self.overlap = bool(overlap)
         self._split = False  # passes are split into edge / interior tiles and the exchange overlaps the interior
-        self._pending = None  # event of the exchange in flight
 
     @property
     def exchange_overlaps(self) -> bool:
@@ -152,7 +153,6 @@ class BandGridSolver:
         """Split every pass into edge and interior tiles when the core can (CUDA) and there is a
         neighbour: the exchange then runs on a second stream beside the interior of a pass."""
         p = self.plan
-        self._pending = None
         self._split = (self.overlap and not self._empty and (p.up is not None or p.down is not None)
                        and hasattr(self.core, "pass_async"))
         if self._split:
@@ -206,23 +206,15 @@ class BandGridSolver:
             core.flip()
 
     def _start_exchange(self) -> None:
-        """Enqueue the halo exchange on the communication stream, ordered after the edge tiles of the
-        pass just enqueued; it moves rows of the buffer that pass writes (current after ``flip``)."""
-        import torch
-
-        core = self.core
-        done = torch.cuda.Event()
-        done.record(core.compute_stream)
-        with torch.cuda.stream(core.comm_stream):
-            core.comm_stream.wait_event(done)
-            self.exchange(which=core.next_buffer())
-            self._pending = torch.cuda.Event()
-            self._pending.record(core.comm_stream)
+        """Start the halo exchange, ordered after the edge tiles of the pass just enqueued; it moves rows
+        of the buffer that pass writes (current after ``flip``).  How "ordered after" and "beside the
+        interior" are realised is the core's business (CUDA: an event and a second stream)."""
+        with self.core.exchange_scope():
+            self.exchange(which=self.core.next_buffer())
 
     def _wait_exchange(self) -> None:
-        if self._pending is not None:
-            self.core.compute_stream.wait_event(self._pending)
-            self._pending = None
+        if self._split:
+            self.core.wait_exchange()
 
     def step(self, iteration: int):
         """Returns ``(uint8 image of this rank's band [rows, m, 3], err[3])``; ``err``
@@ -409,6 +401,7 @@ class CudaBandCore:
         self.compute_stream = (torch.cuda.ExternalStream(h, device=self.torch_device) if h
                                else torch.cuda.default_stream(self.torch_device))
         self.comm_stream = torch.cuda.Stream(self.torch_device)
+        self._pending = None  # event of the exchange in flight
 
     def reset(self, N, mask, tgt, grad):
         self.solver.reset(N, mask, tgt, grad)
@@ -471,6 +464,26 @@ class CudaBandCore:
 
     def next_buffer(self) -> int:
         return self.solver.current_buffer() ^ 1
+
+    @contextlib.contextmanager
+    def exchange_scope(self):
+        """Work enqueued inside runs on the communication stream, after everything the solver's stream
+        holds so far, and concurrently with what the solver enqueues next; ``wait_exchange`` joins."""
+        import torch
+
+        done = torch.cuda.Event()
+        done.record(self.compute_stream)
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(done)
+            yield
+            self._pending = torch.cuda.Event()
+            self._pending.record(self.comm_stream)
+
+    def wait_exchange(self) -> None:
+        """The solver's stream waits (on the device) for the exchange in flight, if any."""
+        if self._pending is not None:
+            self.compute_stream.wait_event(self._pending)
+            self._pending = None
 
 
 def init_process_group_from_env(backend: str | None = None):

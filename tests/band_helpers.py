@@ -1,6 +1,7 @@
 """Shared pieces of the row-band tests: a numpy stand-in core (backed by the
 oracle -- test infrastructure) and an in-process thread transport."""
 
+import contextlib
 import queue
 import threading
 from collections import namedtuple
@@ -14,10 +15,20 @@ from oracle import np_oracle
 class OracleBandCore:
     """Core protocol of ``fpie_b200.band.BandGridSolver`` on the CPU: the slab is
     swept by the numpy oracle with its outer frame held fixed, exactly what the
-    CUDA GridSolver does to a slab."""
+    CUDA GridSolver does to a slab.  Two state buffers and split passes
+    (``set_edge_rows`` / ``pass_async`` / ``flip``) are modelled like the CUDA
+    core's, so the overlapped exchange schedule of ``BandGridSolver`` runs -- and
+    is checked for its ordering -- on the CPU too: a pass over one part computes
+    the sweeps on the whole slab from the CURRENT buffer and commits only that
+    part's rows to the NEXT buffer; an exchange that ran too early or a part that
+    wrote rows it does not own would change the result."""
 
     torch_device = "cpu"
     equ_form = False
+    EDGE, INTERIOR = 0, 1
+
+    def __init__(self, block_k: int = 4):
+        self.block_k = int(block_k)
 
     def set_formulation(self, equ):
         self.equ_form = bool(equ)
@@ -28,8 +39,15 @@ class OracleBandCore:
         m[:, 0] = m[:, -1] = 0  # GridSolver treats the grid frame as unmasked
         self.mask = m
         self.grad = np.array(grad, np.float32, copy=True)
-        self.planes = np.ascontiguousarray(np.asarray(tgt, np.float32).transpose(2, 0, 1))
+        first = np.ascontiguousarray(np.asarray(tgt, np.float32).transpose(2, 0, 1))
+        self.buf = [first, first.copy()]
+        self.cur = 0
         self.window = (0, m.shape[0])
+        self.edge_rows = 0
+
+    @property
+    def planes(self):
+        return self.buf[self.cur]
 
     def reset_slab(self, src, mask, tgt, gradient):
         """uint8 slab images -> the same grid problem the CUDA slab reset builds: the whole slab is the
@@ -59,9 +77,53 @@ class OracleBandCore:
     def _aos(self):
         return self.planes.transpose(1, 2, 0)
 
+    def _swept(self, k):
+        return np_oracle.grid_sweeps(self.mask, self._aos(), self.grad, k).transpose(2, 0, 1)
+
     def sweeps_async(self, k):
-        out = np_oracle.grid_sweeps(self.mask, self._aos(), self.grad, k)
-        self.planes[...] = out.transpose(2, 0, 1)
+        left = int(k)
+        while left > 0:  # passes of block_k, ping-pong like the CUDA core
+            ns = min(left, self.block_k)
+            self.buf[self.cur ^ 1][...] = self._swept(ns)
+            self.cur ^= 1
+            left -= ns
+
+    # -- split passes ----------------------------------------------------------
+    def set_edge_rows(self, rows):
+        self.edge_rows = int(rows)
+
+    def pass_async(self, nsweeps, part):
+        assert 1 <= nsweeps <= self.block_k and self.edge_rows > 0
+        n = self.mask.shape[0]
+        e = min(self.edge_rows, n)
+        edge = np.zeros(n, bool)
+        edge[:e] = edge[n - e :] = True
+        rows = edge if part == self.EDGE else ~edge
+        self.buf[self.cur ^ 1][:, rows] = self._swept(nsweeps)[:, rows]
+
+    def flip(self):
+        self.cur ^= 1
+
+    def next_buffer(self):
+        return self.cur ^ 1
+
+    @contextlib.contextmanager
+    def exchange_scope(self):
+        """Model the asynchronous exchange at its LATEST legal completion: rows received inside the scope
+        land in staging tensors and only reach the halo rows at ``wait_exchange`` -- so a schedule that
+        joins the exchange too late (after tiles that read the halo) computes from stale rows here,
+        just as it could on the GPU."""
+        self._staging = []
+        try:
+            yield
+        finally:
+            self._staged, self._staging = self._staging, None
+
+    def wait_exchange(self):
+        for which, lo, hi, tensors in getattr(self, "_staged", None) or []:
+            for p in range(3):
+                self.buf[which][p, lo:hi] = tensors[p].numpy()
+        self._staged = None
 
     def set_row_window(self, lo, hi):
         self.window = (lo, hi)
@@ -80,8 +142,27 @@ class OracleBandCore:
     def state(self):
         return np.ascontiguousarray(self._aos())
 
-    def rows_view(self, lo, hi):
-        return [torch.from_numpy(self.planes[p, lo:hi]) for p in range(3)]
+    def rows_view(self, lo, hi, which=None):
+        which = self.cur if which is None else which
+        buf = self.buf[which]
+        band_lo, band_hi = self.window
+        if getattr(self, "_staging", None) is not None and (hi <= band_lo or lo >= band_hi):
+            # halo rows requested inside an exchange scope = receive targets: stage them
+            tensors = [torch.empty((hi - lo, buf.shape[2]), dtype=torch.float32) for _ in range(3)]
+            self._staging.append((which, lo, hi, tensors))
+            return tensors
+        return [torch.from_numpy(buf[p, lo:hi]) for p in range(3)]
+
+
+class PlainOracleBandCore(OracleBandCore):
+    """The same core without split passes: ``BandGridSolver`` exchanges between passes."""
+
+    pass_async = None  # ``hasattr`` stays true for None, so hide it properly:
+
+    def __getattribute__(self, name):
+        if name == "pass_async":
+            raise AttributeError(name)
+        return object.__getattribute__(self, name)
 
 
 class ThreadDist:

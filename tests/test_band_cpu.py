@@ -48,7 +48,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, halo, steps, shape, out_dir):
+def _worker(rank, world, port, halo, steps, shape, out_dir, overlap=True, density=0.65):
     for p in (ROOT, PKG_ROOT, os.path.join(ROOT, "tests")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -60,9 +60,10 @@ def _worker(rank, world, port, halo, steps, shape, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        mask, tgt, grad = random_grid(*shape, seed=5, density=0.65)
-        solver = band.BandGridSolver(OracleBandCore(), dist, halo=halo)
+        mask, tgt, grad = random_grid(*shape, seed=5, density=density)
+        solver = band.BandGridSolver(OracleBandCore(block_k=4), dist, halo=halo, overlap=overlap)
         solver.reset(mask.size, mask, tgt, grad)
+        assert solver.exchange_overlaps == overlap  # split passes + exchange beside the interior, or plain
         solver.sync()
         errs = []
         for it in steps:
@@ -75,13 +76,23 @@ def _worker(rank, world, port, halo, steps, shape, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,halo,steps", [(2, 4, (37,)), (2, 16, (5, 20, 12)), (3, 7, (30, 7))])
-def test_gloo_bands_reproduce_global_jacobi(tmp_path, world, halo, steps):
+@pytest.mark.parametrize("world,halo,steps,overlap,density", [
+    (2, 4, (37,), True, 1.0), (2, 8, (5, 20, 12), True, 1.0), (2, 16, (5, 20, 12), True, 1.0), (3, 7, (30, 7), True, 1.0),
+    (2, 16, (5, 20, 12), False, 1.0),
+    (3, 3, (11,), True, 0.65), (2, 16, (40,), True, 0.65)])
+def test_gloo_bands_reproduce_global_jacobi(tmp_path, world, halo, steps, overlap, density):
+    """Row bands over gloo, with the overlapped schedule (halo 4 = one pass per interval, 16 = four
+    passes: first / middle / last, 8 = first / last, 7 and 3 = a short last pass) and with the plain
+    one.  The oracle-backed core completes a scoped exchange only at ``wait_exchange`` (the latest the
+    GPU could), and the fully masked grids with shallow halos are the sensitive cases: a stale halo row
+    moves one row per sweep and fades 4x per row, so an exchange started one pass too early shows at
+    any depth and one joined a pass too late at halo 8 (both checked by mutating the schedule)."""
     shape = (97, 83)
-    mp.spawn(_worker, args=(world, _free_port(), halo, steps, shape, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), halo, steps, shape, str(tmp_path), overlap, density), nprocs=world,
+             join=True)
     from band_helpers import random_grid
 
-    mask, tgt, grad = random_grid(*shape, seed=5, density=0.65)
+    mask, tgt, grad = random_grid(*shape, seed=5, density=density)
     want = np_oracle.grid_sweeps(mask, tgt, grad, sum(steps))
     got = np.zeros_like(want)
     covered = 0
