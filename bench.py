@@ -67,6 +67,21 @@ def profiled_traffic(kernel: str):
         return None
 
 
+def scaling_reference(name: str):
+    """The single-GPU figure of the multi-GPU workload, from the committed scaling record (the N = 1 run of
+    this script measures the headline workload, config 2, not config 4).  None when no record exists."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_scaling_cfg4.json")) as f:
+            rec = json.load(f)
+        if not rec.get("workload", "").startswith(name):
+            return None
+        one = next(r for r in rec["runs"] if r["n_gpus"] == 1)
+        return {"n_gpus": 1, "workload": rec["workload"], "value": one["gupd_per_s"], "unit": "Gupd/s",
+                "source": "profiles/r01_scaling_cfg4.json (python bench.py --workload cfg4)"}
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """Samples SM clocks and throttle reasons with NVML while the timed region runs."""
 
@@ -525,6 +540,8 @@ def run_band(args, work, name):
             "ms_per_step": ms_per_step,
             "higher_is_better": True,
             "scaling": "strong",
+            # strong scaling of ONE fixed problem; its single-GPU figure is not what `--gpus 1` runs (config 2)
+            "scaling_reference": scaling_reference(name) if not (args.size or args.iters) else None,
             "vs_baseline": None,
             "dtype": "f32",
             "data": "synthetic",

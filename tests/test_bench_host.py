@@ -98,3 +98,10 @@ def test_reference_arm_is_silent_on_other_ranks(monkeypatch):
     with redirect_stdout(buf):
         bench.run_reference(SimpleNamespace(steps=1, warmup=0, gpus=2), bench.WORKLOADS["cfg4"], "cfg4")
     assert buf.getvalue() == ""
+
+
+def test_scaling_reference_comes_from_the_committed_record():
+    ref = bench.scaling_reference("cfg4")
+    assert ref is not None and ref["n_gpus"] == 1 and ref["unit"] == "Gupd/s" and ref["value"] > 0
+    assert ref["workload"].startswith("cfg4")
+    assert bench.scaling_reference("cfg2") is None  # the record is of config 4 only
