@@ -71,6 +71,21 @@ API int fpie_b200_device_info(int device, char *name, int name_len, int *sm_coun
   });
 }
 
+API int fpie_b200_host_alloc(int64_t bytes, void **out) {
+  if (!out || bytes < 0) {
+    g_last_error = "fpie_b200_host_alloc: bad arguments";
+    return 4;
+  }
+  *out = nullptr;
+  return guarded([&] { CUDA_CHECK(cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocPortable)); });
+}
+
+API int fpie_b200_host_free(void *ptr) {
+  return guarded([&] {
+    if (ptr) CUDA_CHECK(cudaFreeHost(ptr));
+  });
+}
+
 // ---- GridSolver -----------------------------------------------------------
 API int fpie_b200_grid_create(int device, void *stream, int block_k, int variant, fpie_b200_grid **out) {
   if (!out) {
@@ -139,6 +154,10 @@ API int fpie_b200_grid_sync(fpie_b200_grid *g) {
 API int fpie_b200_grid_fetch(fpie_b200_grid *g, uint8_t *out_img, float *out_err3) {
   NEED(g);
   return guarded([&] { g->impl.fetch(out_img, out_err3); });
+}
+API int fpie_b200_grid_fetch_rows(fpie_b200_grid *g, int row_lo, int row_hi, uint8_t *out_img, float *out_err3) {
+  NEED(g);
+  return guarded([&] { g->impl.fetch(out_img, out_err3, 0, row_lo, row_hi); });
 }
 API int fpie_b200_grid_info(fpie_b200_grid *g, int64_t *unknowns, int64_t *launches, int *block_k,
                             int64_t *active_tiles, int64_t *total_tiles) {

@@ -386,9 +386,12 @@ EquSolver::EquSolver(int device, cudaStream_t stream, int block_size) : device_(
 }
 
 EquSolver::~EquSolver() {
+  int prev = -1;  // (see GridSolver::~GridSolver)
+  cudaGetDevice(&prev);
   cudaSetDevice(device_);
   if (host_err_) cudaFreeHost(host_err_);
   if (host_flag_) cudaFreeHost(host_flag_);
+  if (prev >= 0 && prev != device_) cudaSetDevice(prev);
 }
 
 void EquSolver::require_ready() const { FPIE_REQUIRE(ready_, "EquSolver: step/state called before reset"); }

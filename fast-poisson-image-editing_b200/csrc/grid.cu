@@ -714,10 +714,15 @@ GridSolver::GridSolver(int device, cudaStream_t stream, int block_k, int variant
 }
 
 GridSolver::~GridSolver() {
+  // (runs from Python's garbage collector on whatever thread and current device it happens to be:
+  // restore the caller's device; no exceptions out of a destructor, hence no DeviceGuard)
+  int prev = -1;
+  cudaGetDevice(&prev);
   cudaSetDevice(device_);
   drop_graphs();
   if (cap_stream_) cudaStreamDestroy(cap_stream_);
   if (host_err_) cudaFreeHost(host_err_);
+  if (prev >= 0 && prev != device_) cudaSetDevice(prev);
 }
 
 void GridSolver::configure(int variant, int block_k) {
@@ -800,6 +805,8 @@ void GridSolver::layout(int n, int m) {
   g.wpitch = g.pitch / 32;
   g.groups = (int)ceil_div(m, 4);
   g.plane = (long long)g.rows * g.pitch;
+  // tile descriptors pack the plane row into 28 bits and the plane column into 20 (pack_tile)
+  FPIE_REQUIRE(g.pitch < (1 << 20) && g.rows < (1 << 28), "GridSolver.reset: grid too wide or too tall for the tile descriptors (columns < 2^20, rows < 2^28)");
   geom_ = g;
   win_lo_ = 0;
   win_hi_ = n;
@@ -936,110 +943,133 @@ void GridSolver::build_from_upload() {
   after_state_loaded();
 }
 
+// Everything reset still has to decide once the state is on the device -- fp16 or fp32 gradient stream,
+// blocking depth, tile shape, the list of active tiles -- from ONE round trip: the candidate tilings are
+// classified speculatively, their flags come back together with the unknown count and the fp16 flag,
+// and the host picks.  (Round 1 synchronised five times here.)
 void GridSolver::after_state_loaded() {
-  // fp16 copy of the quarter-gradient (halves that stream when every value is exactly representable)
-  {
-    const long long count = geom_.plane * 3;
-    hq16_.resize((size_t)count);
-    flag_.resize(1);
-    CUDA_CHECK(cudaMemsetAsync(flag_.ptr, 0, sizeof(int), stream_));
-    planes_to_half_kernel<<<blocks_for(count, 256), 256, 0, stream_>>>(count, hq_.ptr, hq16_.ptr, flag_.ptr);
-    CUDA_CHECK(cudaGetLastError());
-    stats_.launches += 1;
-    int inexact = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&inexact, flag_.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream_));
-    // unknown count (stored as a 64-bit integer in err_[3])
-    CUDA_CHECK(cudaMemcpyAsync(host_err_ + 3, err_.ptr + 3, sizeof(double), cudaMemcpyDeviceToHost, stream_));
-    CUDA_CHECK(cudaStreamSynchronize(stream_));
-    h16_ok_ = (inexact == 0) && !force_h32_;
-  }
-  unsigned long long cnt;
-  memcpy(&cnt, host_err_ + 3, sizeof(cnt));
-  stats_.unknowns = (int64_t)cnt;
-  // large and (almost) fully masked grids: every tile is a select-free full tile, and the per-tile cost
-  // amortises better over 12 sweeps than over 8 (measured 894 -> 934 Gupd/s at 4096^2, 2011 -> 2114 on two
-  // 16384 x 32768 bands); masks with a long boundary prefer 8 (fewer partially filled boundary tiles)
-  if (auto_k_ && auto_tune_ && (long long)geom_.n * geom_.m > kModelMaxPixels &&
-      (double)stats_.unknowns >= 0.9 * (double)geom_.n * (double)geom_.m)
-    configure(variant_, 12);
-  if (auto_k_ && auto_tune_ && batch_.batch == 0 && stats_.unknowns > 0 &&
-      (long long)geom_.n * geom_.m <= kModelMaxPixels)
-    choose_by_model();
-  make_tensor_maps();
-  build_tiles();
-  CUDA_CHECK(cudaStreamSynchronize(stream_));
-  cur_ = 0;
-  ready_ = true;
-}
-
-// Small and mid-size grids: count the active tiles of every candidate tiling on the device and take the
-// one with the lowest modelled time per sweep, (waves x per-wave time + launch) / k.
-void GridSolver::choose_by_model() {
   const PlaneGeom &g = geom_;
-  constexpr int NC = (int)(sizeof(kTileChoices) / sizeof(kTileChoices[0]));
-  size_t offset[NC + 1] = {0};
-  int tiles_x[NC], tile_h[NC], hx[NC];
+  // fp16 copy of the quarter-gradient (halves that stream when every value is exactly representable)
+  const long long count = g.plane * 3;
+  hq16_.resize((size_t)count);
+  flag_.resize(1);
+  CUDA_CHECK(cudaMemsetAsync(flag_.ptr, 0, sizeof(int), stream_));
+  planes_to_half_kernel<<<blocks_for(count, 256), 256, 0, stream_>>>(count, hq_.ptr, hq16_.ptr, flag_.ptr);
+  CUDA_CHECK(cudaGetLastError());
+  stats_.launches += 1;
+
+  // candidate (variant, depth) pairs
+  struct Cand {
+    int variant, k, occ;
+    double a, b;
+  };
+  std::vector<Cand> cands;
+  const long long px = (long long)g.n * g.m;
+  const bool free_choice = auto_k_ && auto_tune_;
+  if (free_choice && px > kModelMaxPixels) {
+    cands.push_back({variant_, block_k_, 1, 0, 0});
+    cands.push_back({variant_, 12, 1, 0, 0});  // (picked when the grid is >= 90 % masked, see below)
+  } else if (free_choice && batch_.batch == 0) {
+    for (const TileChoice &c : kTileChoices) cands.push_back({c.variant, c.k, c.occ, c.a, c.b});
+  } else {
+    cands.push_back({variant_, block_k_, 1, 0, 0});
+  }
+  const int NC = (int)cands.size();
+  std::vector<size_t> offset(NC + 1, 0);
+  std::vector<int> tiles_x(NC), tile_h(NC), hx(NC);
   for (int i = 0; i < NC; ++i) {
-    const TileChoice &c = kTileChoices[i];
-    tile_h[i] = shape_for(c.variant).tile_h();
-    hx[i] = (int)round_up(c.k, 4);
+    tile_h[i] = shape_for(cands[i].variant).tile_h();
+    hx[i] = (int)round_up(cands[i].k, 4);
     tiles_x[i] = (int)ceil_div(g.m, TILE_W - 2 * hx[i]);
-    offset[i + 1] = offset[i] + (size_t)tiles_x[i] * ceil_div(g.n, tile_h[i] - 2 * c.k);
+    offset[i + 1] = offset[i] + (size_t)tiles_x[i] * ceil_div(g.n, tile_h[i] - 2 * cands[i].k);
   }
   tile_flags_.resize(offset[NC]);
   for (int i = 0; i < NC; ++i) {
-    const TileChoice &c = kTileChoices[i];
     const int n_i = (int)(offset[i + 1] - offset[i]);
-    classify_tiles_kernel<<<n_i, 256, 0, stream_>>>(g, bits_.ptr, tiles_x[i], tile_h[i], tile_h[i] - 2 * c.k,
-                                                    TILE_W - 2 * hx[i], c.k, hx[i], tile_flags_.ptr + offset[i]);
+    classify_tiles_kernel<<<n_i, 256, 0, stream_>>>(g, bits_.ptr, tiles_x[i], tile_h[i], tile_h[i] - 2 * cands[i].k,
+                                                    TILE_W - 2 * hx[i], cands[i].k, hx[i], tile_flags_.ptr + offset[i]);
   }
   CUDA_CHECK(cudaGetLastError());
   stats_.launches += NC;
   std::vector<uint32_t> flags(offset[NC]);
+  int inexact = 0;
   CUDA_CHECK(cudaMemcpyAsync(flags.data(), tile_flags_.ptr, flags.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                              stream_));
+  CUDA_CHECK(cudaMemcpyAsync(&inexact, flag_.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+  // unknown count (stored as a 64-bit integer in err_[3])
+  CUDA_CHECK(cudaMemcpyAsync(host_err_ + 3, err_.ptr + 3, sizeof(double), cudaMemcpyDeviceToHost, stream_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));
-  int best = -1;
-  double best_cost = 0.0;
-  for (int i = 0; i < NC; ++i) {
-    const TileChoice &c = kTileChoices[i];
-    long long active = 0;
-    for (size_t t = offset[i]; t < offset[i + 1]; ++t) active += flags[t] & 1u;
-    const long long slots = (long long)sm_count_ * c.occ, items = 3 * active;
-    const long long full = items / slots, rest = items - full * slots;
-    double waves = (double)full;
-    if (rest > 0) waves += (c.occ == 2 && rest <= sm_count_) ? kLoneCtaWave : 1.0;
-    const double cost = (waves * (c.a + c.b * c.k) + kLaunchUs) / c.k;
-    if (best < 0 || cost < best_cost) best = i, best_cost = cost;
+  h16_ok_ = (inexact == 0) && !force_h32_;
+  unsigned long long cnt;
+  memcpy(&cnt, host_err_ + 3, sizeof(cnt));
+  stats_.unknowns = (int64_t)cnt;
+
+  int best = 0;
+  if (free_choice && px > kModelMaxPixels) {
+    // large and (almost) fully masked grids: every tile is a select-free full tile, and the per-tile cost
+    // amortises better over 12 sweeps than over 8 (measured 894 -> 934 Gupd/s at 4096^2, 2011 -> 2114 on two
+    // 16384 x 32768 bands); masks with a long boundary prefer 8 (fewer partially filled boundary tiles)
+    best = ((double)stats_.unknowns >= 0.9 * (double)g.n * (double)g.m) ? 1 : 0;
+  } else if (free_choice && batch_.batch == 0 && stats_.unknowns > 0) {
+    // small and mid-size grids: the lowest modelled time per sweep, (waves x per-wave time + launch) / k,
+    // from the number of active tiles of every candidate tiling
+    double best_cost = 0.0;
+    best = -1;
+    for (int i = 0; i < NC; ++i) {
+      long long active = 0;
+      for (size_t t = offset[i]; t < offset[i + 1]; ++t) active += flags[t] & 1u;
+      const long long slots = (long long)sm_count_ * cands[i].occ, items = 3 * active;
+      const long long full = items / slots, rest = items - full * slots;
+      double waves = (double)full;
+      if (rest > 0) waves += (cands[i].occ == 2 && rest <= sm_count_) ? kLoneCtaWave : 1.0;
+      const double cost = (waves * (cands[i].a + cands[i].b * cands[i].k) + kLaunchUs) / cands[i].k;
+      if (best < 0 || cost < best_cost) best = i, best_cost = cost;
+    }
+  } else if (free_choice && batch_.batch == 0) {
+    best = -1;  // no unknowns: keep the size-based configuration
   }
-  configure(kTileChoices[best].variant, kTileChoices[best].k);
+  if (best >= 0 && (cands[best].variant != variant_ || cands[best].k != block_k_)) configure(cands[best].variant, cands[best].k);
+  if (best < 0) {  // (the flags of the current configuration are not among the candidates: classify it)
+    build_tiles(nullptr);
+  } else {
+    build_tiles(flags.data() + offset[best]);
+  }
+  make_tensor_maps();
+  cur_ = 0;
+  ready_ = true;
 }
 
-void GridSolver::build_tiles() {
+// The active-tile list of the current configuration, from its classification flags (classified here
+// when the caller has none).
+void GridSolver::build_tiles(const uint32_t *flags_in) {
   const PlaneGeom &g = geom_;
   const int step_x = TILE_W - 2 * halo_x_, step_y = shape_.tile_h() - 2 * block_k_;
   const int tiles_x = (int)ceil_div(g.m, step_x), tiles_y = (int)ceil_div(g.n, step_y);
   const int ntiles = tiles_x * tiles_y;
-  tile_flags_.resize(ntiles);
-  classify_tiles_kernel<<<ntiles, 256, 0, stream_>>>(g, bits_.ptr, tiles_x, shape_.tile_h(), step_y, step_x, block_k_,
-                                                     halo_x_, tile_flags_.ptr);
-  CUDA_CHECK(cudaGetLastError());
-  stats_.launches += 1;
-  std::vector<uint32_t> flags(ntiles);
-  CUDA_CHECK(cudaMemcpyAsync(flags.data(), tile_flags_.ptr, ntiles * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
-  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  std::vector<uint32_t> own;
+  if (!flags_in) {
+    tile_flags_.resize(ntiles);
+    classify_tiles_kernel<<<ntiles, 256, 0, stream_>>>(g, bits_.ptr, tiles_x, shape_.tile_h(), step_y, step_x, block_k_,
+                                                       halo_x_, tile_flags_.ptr);
+    CUDA_CHECK(cudaGetLastError());
+    stats_.launches += 1;
+    own.resize(ntiles);
+    CUDA_CHECK(cudaMemcpyAsync(own.data(), tile_flags_.ptr, ntiles * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    flags_in = own.data();
+  }
   std::vector<int2> &list = host_tiles_;
   list.clear();
   host_tile_row_.clear();
   list.reserve((size_t)ntiles * 3);
   int64_t active = 0;
   for (int t = 0; t < ntiles; ++t) {
-    if (!(flags[t] & 1u)) continue;
+    if (!(flags_in[t] & 1u)) continue;
     ++active;
     const int ty = t / tiles_x, tx = t % tiles_x;
     for (int ch = 0; ch < 3; ++ch) {
       list.push_back(pack_tile(g.padr + ty * step_y - block_k_, g.padc + tx * step_x - halo_x_, ch,
-                               (flags[t] & 2u) ? 1 : 0));
+                               (flags_in[t] & 2u) ? 1 : 0));
       host_tile_row_.push_back(ty);
     }
   }
@@ -1050,9 +1080,9 @@ void GridSolver::build_tiles() {
   stats_.total_tiles = ntiles;
   n_tile_entries_ = (int)list.size();
   tiles_.resize(std::max<size_t>(list.size(), 1));
+  // (pageable source: the driver stages the bytes before the call returns, and host_tiles_ outlives it anyway)
   if (!list.empty())
     CUDA_CHECK(cudaMemcpyAsync(tiles_.ptr, list.data(), list.size() * sizeof(int2), cudaMemcpyHostToDevice, stream_));
-  CUDA_CHECK(cudaStreamSynchronize(stream_));
 }
 
 namespace {
@@ -1118,9 +1148,9 @@ void launch_pipe(const SweepArgs &a) {
     launch_pipe_h<R, NW, OCC, false>(a);
 }
 
-template <int R, int NW, bool H16>
+template <int R, int NW, int OCC, bool H16>
 void launch_pair_h(const SweepArgs &a) {
-  auto kernel = grid_sweepk_pair_kernel<R, NW, H16>;
+  auto kernel = grid_sweepk_pair_kernel<R, NW, OCC, H16>;
   constexpr size_t smem = PairSmem<R, NW, H16>::TOTAL;
   static int configured_device = -1;
   int dev = 0;
@@ -1129,17 +1159,26 @@ void launch_pair_h(const SweepArgs &a) {
     CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured_device = dev;
   }
-  const int grid = std::min(a.ntiles, a.grid);
-  kernel<<<grid, NW * 32, smem, a.stream>>>(*a.tm_x, *a.tm_h, *a.tm_m, a.g, a.xout, a.tiles, a.ntiles, a.nsweeps,
-                                            a.halo_y, a.halo_x);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(std::min(a.ntiles, a.grid * OCC));
+  cfg.blockDim = dim3(NW * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = a.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // (see launch_pipe_h)
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (a.ntiles >= a.grid) ? 1 : 0;
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, *a.tm_x, *a.tm_h, *a.tm_m, a.g, a.xout, a.tiles, a.ntiles, a.nsweeps,
+                                a.halo_y, a.halo_x, a.reverse));
 }
 
-template <int R, int NW>
+template <int R, int NW, int OCC>
 void launch_pair(const SweepArgs &a) {
   if (a.h16)
-    launch_pair_h<R, NW, true>(a);
+    launch_pair_h<R, NW, OCC, true>(a);
   else
-    launch_pair_h<R, NW, false>(a);
+    launch_pair_h<R, NW, OCC, false>(a);
 }
 
 struct VariantInfo {
@@ -1149,14 +1188,28 @@ struct VariantInfo {
 
 // kernel variants (fpie_b200_grid_create `variant`): register-tile shape
 // rows/thread x warps, CTAs per SM; "pipe" = TMA-staged + split-phase exchange.
+// The default build carries the shapes the solver picks by itself plus the cross-check kernels;
+// -DFPIE_ALL_VARIANTS adds the measured-and-dominated shapes of DESIGN.md section 5 (test / tuning builds).
 VariantInfo variant_info(int v) {
   switch (v) {
     case 0:  // (automatic: replaced by a concrete shape at reset)
     case 39: return {14, 12, 1, true};
     case 1: return {16, 12, 1, false};  // (tile shape unused: one sweep per launch)
+    case 4: return {16, 12, 1, false};  // direct global -> register loads, no TMA staging
+    case 12: return {8, 8, 2, true};
+    // two warps per scheduler: each sub-partition's 16384 registers then allow up to 255 per thread
+    case 24: return {21, 8, 1, true};
+    // four warps per CTA, several CTAs per SM: small tiles for small grids without giving up rows per thread
+    case 36: return {21, 4, 2, true};
+    // packed-pair (FFMA2) kernels: rows = 2 x pair-rows per thread
+    case 40: return {22, 8, 1, true};
+    case 41: return {20, 8, 1, true};
+    case 42: return {20, 4, 2, true};
+    case 43: return {14, 12, 1, true};
+    case 44: return {10, 16, 1, true};
+#ifdef FPIE_ALL_VARIANTS
     case 2: return {16, 8, 1, false};
     case 3: return {8, 16, 1, false};
-    case 4: return {16, 12, 1, false};
     case 5: return {16, 12, 1, true};
     case 6: return {16, 6, 2, true};
     case 7: return {14, 6, 2, true};
@@ -1164,21 +1217,16 @@ VariantInfo variant_info(int v) {
     case 9: return {12, 14, 1, true};
     case 10: return {10, 16, 1, true};
     case 11: return {8, 16, 1, true};
-    case 12: return {8, 8, 2, true};
     case 17: return {15, 12, 1, true};
-    // two warps per scheduler: each sub-partition's 16384 registers then allow up to 255 per thread
     case 18: return {20, 8, 1, true};
-    case 24: return {21, 8, 1, true};
     case 25: return {19, 8, 1, true};
-    // four warps per CTA, several CTAs per SM: small tiles for small grids without giving up rows per thread
     case 29: return {16, 4, 2, true};
-    case 36: return {21, 4, 2, true};
     case 37: return {12, 4, 3, true};
-    // packed-pair (FFMA2) kernels: rows = 2 x pair-rows per thread
     case 20: return {14, 12, 1, true};
     case 21: return {16, 12, 1, true};
     case 22: return {12, 12, 1, true};
-    default: throw Error("fpie_b200: unknown grid kernel variant");
+#endif
+    default: throw Error("fpie_b200: unknown grid kernel variant (dominated shapes need a -DFPIE_ALL_VARIANTS build)");
   }
 }
 
@@ -1186,9 +1234,18 @@ VariantInfo variant_info(int v) {
 static void launch_variant(int variant, const SweepArgs &a) {
   switch (variant) {
     case 39: launch_pipe<14, 12, 1>(a); break;
+    case 4: launch_direct<16, 12>(a); break;
+    case 12: launch_pipe<8, 8, 2>(a); break;
+    case 24: launch_pipe<21, 8, 1>(a); break;
+    case 36: launch_pipe<21, 4, 2>(a); break;
+    case 40: launch_pair<11, 8, 1>(a); break;
+    case 41: launch_pair<10, 8, 1>(a); break;
+    case 42: launch_pair<10, 4, 2>(a); break;
+    case 43: launch_pair<7, 12, 1>(a); break;
+    case 44: launch_pair<5, 16, 1>(a); break;
+#ifdef FPIE_ALL_VARIANTS
     case 2: launch_direct<16, 8>(a); break;
     case 3: launch_direct<8, 16>(a); break;
-    case 4: launch_direct<16, 12>(a); break;
     case 5: launch_pipe<16, 12, 1>(a); break;
     case 6: launch_pipe<16, 6, 2>(a); break;
     case 7: launch_pipe<14, 6, 2>(a); break;
@@ -1196,18 +1253,16 @@ static void launch_variant(int variant, const SweepArgs &a) {
     case 9: launch_pipe<12, 14, 1>(a); break;
     case 10: launch_pipe<10, 16, 1>(a); break;
     case 11: launch_pipe<8, 16, 1>(a); break;
-    case 12: launch_pipe<8, 8, 2>(a); break;
     case 17: launch_pipe<15, 12, 1>(a); break;
     case 18: launch_pipe<20, 8, 1>(a); break;
-    case 24: launch_pipe<21, 8, 1>(a); break;
     case 25: launch_pipe<19, 8, 1>(a); break;
     case 29: launch_pipe<16, 4, 2>(a); break;
-    case 36: launch_pipe<21, 4, 2>(a); break;
     case 37: launch_pipe<12, 4, 3>(a); break;
-    case 20: launch_pair<7, 12>(a); break;
-    case 21: launch_pair<8, 12>(a); break;
-    case 22: launch_pair<6, 12>(a); break;
-    default: throw Error("fpie_b200: unknown grid kernel variant");
+    case 20: launch_pair<7, 12, 1>(a); break;
+    case 21: launch_pair<8, 12, 1>(a); break;
+    case 22: launch_pair<6, 12, 1>(a); break;
+#endif
+    default: throw Error("fpie_b200: unknown grid kernel variant (dominated shapes need a -DFPIE_ALL_VARIANTS build)");
   }
 }
 
@@ -1413,18 +1468,21 @@ void GridSolver::sync() {
   CUDA_CHECK(cudaStreamSynchronize(stream_));
 }
 
-void GridSolver::fetch(uint8_t *out_img, float *out_err3, int64_t row_stride) {
+void GridSolver::fetch(uint8_t *out_img, float *out_err3, int64_t row_stride, int row_lo, int row_hi) {
   require_ready();
   DeviceGuard guard(device_);
+  if (row_hi < 0) row_hi = geom_.n;
+  FPIE_REQUIRE(0 <= row_lo && row_lo <= row_hi && row_hi <= geom_.n, "fetch: row range outside the grid");
+  FPIE_REQUIRE(batch_.batch == 0 || (row_lo == 0 && row_hi == geom_.n), "fetch: row ranges are not available for batched patches");
   const size_t row_bytes = (size_t)geom_.m * 3;
   if (row_stride <= 0) row_stride = (int64_t)row_bytes;
   FPIE_REQUIRE((size_t)row_stride >= row_bytes, "fetch: destination row stride is smaller than a row");
   if (out_img && batch_.batch > 0)  // [batch, ph, pw, 3], packed
     CUDA_CHECK(cudaMemcpyAsync(out_img, img_.ptr, (size_t)batch_.batch * batch_.ph * batch_.pw * 3,
                                cudaMemcpyDeviceToHost, stream_));
-  else if (out_img)
-    CUDA_CHECK(cudaMemcpy2DAsync(out_img, (size_t)row_stride, img_.ptr, row_bytes, row_bytes, geom_.n,
-                                 cudaMemcpyDeviceToHost, stream_));
+  else if (out_img && row_hi > row_lo)
+    CUDA_CHECK(cudaMemcpy2DAsync(out_img, (size_t)row_stride, img_.ptr + (size_t)row_lo * row_bytes, row_bytes, row_bytes,
+                                 row_hi - row_lo, cudaMemcpyDeviceToHost, stream_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));
   if (out_err3) {
     if (batch_.batch > 0) {  // [batch, 3]

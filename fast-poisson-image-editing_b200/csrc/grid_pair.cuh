@@ -1,13 +1,19 @@
 // Packed-pair variant of the temporally blocked GridSolver kernel (sm_100a FFMA2).
 //
 // Blackwell adds `fma.rn.f32x2` (SASS FFMA2): one instruction, two independent fp32 FMAs on a
-// 64-bit register pair.  The FMA pipe rate is unchanged, but the instruction count of the sweep
-// -- what bounds the scalar kernel -- drops by ~40 %.  The two lanes of a pair must be lattice
-// sites with identical neighbour structure, so a thread pairs row r of the tile's UPPER half with
-// row r + TH/2 of its LOWER half (same columns): up / down / left / right neighbours of a pair are
-// again aligned pairs, except across the seam between the halves, which the first / last warp
-// patch by reading the other end's mailbox row with swapped components.  The tile, its halo
-// logic, the TMA staging and the HBM layout are exactly those of the scalar kernel.
+// 64-bit register pair.  The FMA pipe rate is unchanged (tools/probes/issue_probe.cu: 125 of 128
+// lanes per clock and SM at half the issue slots of scalar FFMA), so the instruction count of the
+// sweep -- what bounds the scalar kernel -- drops by ~40 % and the sweep becomes FMA-pipe bound.
+// The two lanes of a pair must be lattice sites with identical neighbour structure, so a thread
+// pairs row r of the tile's UPPER half with row r + TH/2 of its LOWER half (same columns): up /
+// down / left / right neighbours of a pair are again aligned pairs, except across the seam
+// between the halves, which the first / last warp patch by reading the other end's mailbox row
+// with swapped components.  The tile, its halo logic, the TMA staging, the programmatic dependent
+// launch and the HBM layout are exactly those of the scalar kernel (grid.cu).
+//
+// With two warps per scheduler nothing hides a shuffle's latency but the thread's own independent
+// work, so the left / right neighbour shuffles of a row are issued kShuffleAhead rows before the
+// row is updated (they read old values: Jacobi).
 #pragma once
 
 #include "tma.cuh"
@@ -52,6 +58,15 @@ struct alignas(16) PairRow {
   pair64 p[4];  // 4 pixels; .lo = row in the upper half, .hi = same row of the lower half
 };
 
+// mask nibbles of a thread's R pair-rows, 8 rows per word, upper / lower half
+template <int R>
+struct PairMask {
+  static constexpr int W = (R + 7) / 8;
+  uint32_t lo[W], hi[W];
+  __device__ __forceinline__ uint32_t nib_lo(int i) const { return lo[i / 8] >> ((i % 8) * 4); }
+  __device__ __forceinline__ uint32_t nib_hi(int i) const { return hi[i / 8] >> ((i % 8) * 4); }
+};
+
 // both components: ((((g + U) + D) + L) + R) / 4 on quarter-scaled operands (see jacobi_q)
 __device__ __forceinline__ pair64 jacobi_q2(pair64 hq, pair64 up, pair64 dn, pair64 lf, pair64 rt, pair64 q) {
   pair64 t = ffma2(up, q, hq);
@@ -60,12 +75,11 @@ __device__ __forceinline__ pair64 jacobi_q2(pair64 hq, pair64 up, pair64 dn, pai
   return ffma2(rt, q, t);
 }
 
+// one pair-row; lf / rt = the left neighbour of pixel 0 / right neighbour of pixel 3 (already shuffled)
 template <bool MIXED>
 __device__ __forceinline__ void pair_row_update(PairRow &xi, const PairRow &hi, const PairRow &prev, const PairRow &nxt,
-                                                uint32_t nib_lo, uint32_t nib_hi, pair64 q) {
+                                                pair64 lf, pair64 rt, uint32_t nib_lo, uint32_t nib_hi, pair64 q) {
   const PairRow cur = xi;
-  const pair64 lf = shfl_up_pair(cur.p[3]);
-  const pair64 rt = shfl_down_pair(cur.p[0]);
   PairRow o;
   o.p[0] = jacobi_q2(hi.p[0], prev.p[0], nxt.p[0], lf, cur.p[1], q);
   o.p[1] = jacobi_q2(hi.p[1], prev.p[1], nxt.p[1], cur.p[0], cur.p[2], q);
@@ -85,9 +99,15 @@ __device__ __forceinline__ void pair_row_update(PairRow &xi, const PairRow &hi, 
   xi = o;
 }
 
-// One sweep over the R pair-rows of a thread (= 2R tile rows), split-phase like tile_sweep_split.
+#ifndef FPIE_SHUFFLE_AHEAD
+#define FPIE_SHUFFLE_AHEAD 2
+#endif
+constexpr int kShuffleAhead = FPIE_SHUFFLE_AHEAD;
+
+// One sweep over the R pair-rows of a thread (= 2R tile rows), split-phase like tile_sweep_split:
+// publish the strip's edge pair-rows, arrive, update the interior, then wait for the neighbours.
 template <int R, int NW, bool MIXED>
-__device__ __forceinline__ void pair_sweep(PairRow (&x)[R], const PairRow (&h)[R], uint32_t mb_lo, uint32_t mb_hi,
+__device__ __forceinline__ void pair_sweep(PairRow (&x)[R], const PairRow (&h)[R], const PairMask<R> &mb,
                                            PairRow (*mailbox)[2][NW][32], uint64_t *mail_bar, int parity,
                                            uint32_t &mphase, pair64 q) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -98,10 +118,25 @@ __device__ __forceinline__ void pair_sweep(PairRow (&x)[R], const PairRow (&h)[R
   const PairRow first_old = x[1];
   PairRow prev = x[0];
   PairRow up, dn;
-  constexpr int PULL_ROW = (R >= 6) ? R - 3 : R - 2;
+  pair64 lf[R], rt[R];  // (fully unrolled: only the rows in flight are live)
+  constexpr int PULL_ROW = (R >= 9) ? R - 4 : (R >= 6) ? R - 3 : R - 2;
+  constexpr int LOOK = kShuffleAhead;
+#pragma unroll
+  for (int i = 1; i < 1 + LOOK && i < R - 1; ++i) {
+    lf[i] = shfl_up_pair(x[i].p[3]);
+    rt[i] = shfl_down_pair(x[i].p[0]);
+  }
 #pragma unroll
   for (int i = 1; i < R - 1; ++i) {
+    if (i + LOOK < R - 1) {  // rows below i still hold the previous sweep's values
+      lf[i + LOOK] = shfl_up_pair(x[i + LOOK].p[3]);
+      rt[i + LOOK] = shfl_down_pair(x[i + LOOK].p[0]);
+    }
     if (i == PULL_ROW) {
+      lf[0] = shfl_up_pair(x[0].p[3]);
+      rt[0] = shfl_down_pair(x[0].p[0]);
+      lf[R - 1] = shfl_up_pair(x[R - 1].p[3]);
+      rt[R - 1] = shfl_down_pair(x[R - 1].p[0]);
       mbar_wait(&mail_bar[parity], (mphase >> parity) & 1u);
       mphase ^= 1u << parity;
       // row above the strip: the previous warp's last pair-row; for warp 0 the upper half has no row
@@ -119,11 +154,11 @@ __device__ __forceinline__ void pair_sweep(PairRow (&x)[R], const PairRow (&h)[R
       }
     }
     const PairRow cur = x[i];
-    pair_row_update<MIXED>(x[i], h[i], prev, x[i + 1], mb_lo >> (4 * i), mb_hi >> (4 * i), q);
+    pair_row_update<MIXED>(x[i], h[i], prev, x[i + 1], lf[i], rt[i], mb.nib_lo(i), mb.nib_hi(i), q);
     prev = cur;
   }
-  pair_row_update<MIXED>(x[0], h[0], up, first_old, mb_lo, mb_hi, q);
-  pair_row_update<MIXED>(x[R - 1], h[R - 1], prev, dn, mb_lo >> (4 * (R - 1)), mb_hi >> (4 * (R - 1)), q);
+  pair_row_update<MIXED>(x[0], h[0], up, first_old, lf[0], rt[0], mb.nib_lo(0), mb.nib_hi(0), q);
+  pair_row_update<MIXED>(x[R - 1], h[R - 1], prev, dn, lf[R - 1], rt[R - 1], mb.nib_lo(R - 1), mb.nib_hi(R - 1), q);
 }
 
 // Shared-memory layout: staging as in PipeSmem (tile of 2*R*NW rows), mailbox of pair-rows.
@@ -142,12 +177,11 @@ struct PairSmem {
   static constexpr uint32_t TOTAL = MAIL_OFF + 2 * 2 * NW * 32 * sizeof(PairRow);
 };
 
-template <int R, int NW, bool H16>
-__global__ void __launch_bounds__(NW * 32, 1)
+template <int R, int NW, int OCC, bool H16>
+__global__ void __launch_bounds__(NW * 32, OCC)
 grid_sweepk_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h,
                         const __grid_constant__ CUtensorMap tm_m, PlaneGeom g, float *__restrict__ xout,
-                        const int2 *__restrict__ tiles, int ntiles, int nsweeps, int halo_y, int halo_x) {
-  static_assert(R <= 8, "mask bits of one half must fit a 32-bit word");
+                        const int2 *__restrict__ tiles, int ntiles, int nsweeps, int halo_y, int halo_x, int reverse) {
   constexpr int HH = R * NW;  // rows per half
   constexpr int TH = 2 * HH;
   using L = PairSmem<R, NW, H16>;
@@ -181,20 +215,25 @@ grid_sweepk_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
   int t = blockIdx.x;
   if (t >= ntiles) return;
   const int stride = gridDim.x;
-  int2 cur = tiles[t];
-  int2 nxt = (t + stride < ntiles) ? tiles[t + stride] : cur;
+  if (reverse) tiles += ntiles - 1;  // alternate passes walk the list backwards (L2 reuse, see the scalar kernel)
+  const int dir = reverse ? -1 : 1;
+  int2 cur = tiles[dir * t];
+  int2 nxt = (t + stride < ntiles) ? tiles[dir * (t + stride)] : cur;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (threadIdx.x == 0) issue(cur);
   int parity = 0;
   uint32_t phase = 0, mphase = 0;
   for (; t < ntiles; t += stride) {
-    const int2 nxt2 = (t + 2 * stride < ntiles) ? tiles[t + 2 * stride] : nxt;
+    const int2 nxt2 = (t + 2 * stride < ntiles) ? tiles[dir * (t + 2 * stride)] : nxt;
     const TileRef td = unpack_tile(cur);
     const int pcol = td.pcol + 4 * lane;
     // global offsets of the thread's first row in the upper / lower half
     const long long base_lo = (long long)td.plane * g.plane + (long long)(td.prow + w * R) * g.pitch + pcol;
-    const long long base_hi = base_lo + (long long)HH * g.pitch;
     PairRow x[R], h[R];
-    uint32_t mb_lo = td.full ? 0xffffffffu : 0u, mb_hi = mb_lo;
+    PairMask<R> mb;
+#pragma unroll
+    for (int i = 0; i < PairMask<R>::W; ++i) mb.lo[i] = mb.hi[i] = td.full ? 0xffffffffu : 0u;
 
     mbar_wait(&bars[0], phase);
     phase ^= 1;
@@ -242,8 +281,8 @@ grid_sweepk_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         const uint32_t *mhi = mlo + HH * MASK_BOX_WORDS;
 #pragma unroll
         for (int i = 0; i < R; ++i) {
-          mb_lo |= ((mlo[i * MASK_BOX_WORDS] >> (pcol & 31)) & 0xFu) << (4 * i);
-          mb_hi |= ((mhi[i * MASK_BOX_WORDS] >> (pcol & 31)) & 0xFu) << (4 * i);
+          mb.lo[i / 8] |= ((mlo[i * MASK_BOX_WORDS] >> (pcol & 31)) & 0xFu) << ((i % 8) * 4);
+          mb.hi[i / 8] |= ((mhi[i * MASK_BOX_WORDS] >> (pcol & 31)) & 0xFu) << ((i % 8) * 4);
         }
       }
     }
@@ -253,9 +292,9 @@ grid_sweepk_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
 #pragma unroll 2
     for (int s = 0; s < nsweeps; ++s) {
       if (td.full)
-        pair_sweep<R, NW, false>(x, h, mb_lo, mb_hi, mailbox, &bars[1], parity, mphase, q);
+        pair_sweep<R, NW, false>(x, h, mb, mailbox, &bars[1], parity, mphase, q);
       else
-        pair_sweep<R, NW, true>(x, h, mb_lo, mb_hi, mailbox, &bars[1], parity, mphase, q);
+        pair_sweep<R, NW, true>(x, h, mb, mailbox, &bars[1], parity, mphase, q);
       parity ^= 1;
     }
 
@@ -264,11 +303,11 @@ grid_sweepk_pair_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
       const bool lane_ok = (4 * lane >= halo_x) && (4 * lane < TILE_W - halo_x);
       const uint32_t pitch_bytes = (uint32_t)g.pitch * 4u;
       char *out_lo = reinterpret_cast<char *>(xout + base_lo);
-      char *out_hi = reinterpret_cast<char *>(xout + base_hi);
+      char *out_hi = out_lo + (size_t)HH * pitch_bytes;
 #pragma unroll
       for (int i = 0; i < R; ++i) {
         const int tr_lo = w * R + i, tr_hi = HH + w * R + i;
-        const uint32_t nl = td.full ? 1u : (mb_lo >> (4 * i)) & 0xFu, nh = td.full ? 1u : (mb_hi >> (4 * i)) & 0xFu;
+        const uint32_t nl = td.full ? 1u : mb.nib_lo(i) & 0xFu, nh = td.full ? 1u : mb.nib_hi(i) & 0xFu;
         const float4 a = make_float4(lo2(x[i].p[0]), lo2(x[i].p[1]), lo2(x[i].p[2]), lo2(x[i].p[3]));
         const float4 b = make_float4(hi2(x[i].p[0]), hi2(x[i].p[1]), hi2(x[i].p[2]), hi2(x[i].p[3]));
         st4_if(out_lo + (size_t)i * pitch_bytes, a, lane_ok && tr_lo >= halo_y && nl);

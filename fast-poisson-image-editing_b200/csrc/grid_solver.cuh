@@ -63,7 +63,7 @@ class GridSolver {
   void sweeps_async(int iters);
   void finish_async();
   void sync();
-  void fetch(uint8_t *out_img, float *out_err3, int64_t row_stride = 0);
+  void fetch(uint8_t *out_img, float *out_err3, int64_t row_stride = 0, int row_lo = 0, int row_hi = -1);
   void step(int iters, uint8_t *out_img, float *out_err3, int64_t row_stride = 0);
   int solve(int max_iters, int check_every, float tol, float *out_err3);
   void state(float *out);
@@ -85,12 +85,11 @@ class GridSolver {
  private:
   void require_ready() const;
   void layout(int n, int m);
-  void build_tiles();
+  void build_tiles(const uint32_t *flags);
   void after_state_loaded();
   void make_tensor_maps();
   void configure(int variant, int block_k);
   void auto_configure(int n, int m);
-  void choose_by_model();
   void drop_graphs();
   void build_from_upload();
   static TileShape shape_for(int variant);

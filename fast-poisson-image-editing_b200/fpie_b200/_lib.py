@@ -24,6 +24,8 @@ i32p, f32p, u8p, i64p, intp = P(ctypes.c_int32), P(ctypes.c_float), P(ctypes.c_u
 SIGNATURES = {
     "fpie_b200_abi_version": [],
     "fpie_b200_device_count": [],
+    "fpie_b200_host_alloc": [c_i64, ctypes.POINTER(c_void_p)],
+    "fpie_b200_host_free": [c_void_p],
     "fpie_b200_device_info": [c_int, ctypes.c_char_p, c_int, intp, intp, intp],
     "fpie_b200_grid_create": [c_int, c_void_p, c_int, c_int, P(c_void_p)],
     "fpie_b200_grid_destroy": [c_void_p],
@@ -41,6 +43,7 @@ SIGNATURES = {
     "fpie_b200_grid_finish_async": [c_void_p],
     "fpie_b200_grid_sync": [c_void_p],
     "fpie_b200_grid_fetch": [c_void_p, u8p, f32p],
+    "fpie_b200_grid_fetch_rows": [c_void_p, c_int, c_int, u8p, f32p],
     "fpie_b200_grid_info": [c_void_p, i64p, i64p, intp, i64p, i64p],
     "fpie_b200_grid_reset_from_images": [c_void_p, u8p, c_int, c_int, u8p, c_int, c_int, c_int, u8p, c_int, c_int,
                                          c_int, c_int, c_int, c_int, c_int, i64p, i32p],
@@ -104,13 +107,50 @@ def check(rc: int) -> None:
         raise RuntimeError(msg or f"fpie_b200 call failed with status {rc}")
 
 
-def current_stream_handle(device: int) -> int:
-    """The raw cudaStream_t of torch's current stream on ``device`` (0 = the
-    default stream when torch is not importable)."""
+class _PinnedBlock:
+    """Page-locked host bytes owned by the C ABI (``fpie_b200_host_alloc``).  numpy arrays made from it
+    keep it as their ``base``; the memory is released when the last of them is gone."""
+
+    def __init__(self, nbytes: int):
+        self._lib = load()
+        self._ptr = c_void_p()
+        check(self._lib.fpie_b200_host_alloc(int(nbytes), ctypes.byref(self._ptr)))
+        self.__array_interface__ = {"shape": (max(int(nbytes), 1),), "typestr": "|u1",
+                                    "data": (self._ptr.value, False), "version": 3}
+
+    def __del__(self):
+        try:
+            if self._ptr:
+                self._lib.fpie_b200_host_free(self._ptr)
+                self._ptr = c_void_p()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """``np.empty(shape, dtype)`` in page-locked host memory."""
+    import numpy as np
+
+    shape = tuple(int(v) for v in shape)
+    count = int(np.prod(shape, dtype=np.int64))
+    nbytes = count * np.dtype(dtype).itemsize
+    raw = np.asarray(_PinnedBlock(nbytes))
+    return raw[:nbytes].view(dtype).reshape(shape)
+
+
+def current_stream(device: int):
+    """``(torch Stream object or None, raw cudaStream_t)`` of torch's current stream on ``device``
+    (``(None, 0)`` = the default stream when torch is not importable).  Whoever hands the raw handle
+    to the C ABI must keep the Stream object alive for as long as the handle is in use."""
     try:
         import torch
     except ImportError:
-        return 0
+        return None, 0
     if not torch.cuda.is_available():
-        return 0
-    return int(torch.cuda.current_stream(device).cuda_stream)
+        return None, 0
+    stream = torch.cuda.current_stream(device)
+    return stream, int(stream.cuda_stream)
+
+
+def current_stream_handle(device: int) -> int:
+    return current_stream(device)[1]

@@ -226,9 +226,12 @@ class BandGridSolver:
             img, err = np.zeros((0, 0, 3), np.uint8), np.zeros(3, np.float32)
         else:
             self.core.finish_async()
-            slab_img, err = self.core.fetch()
             lo, hi = self.plan.local_band
-            img = slab_img[lo:hi]
+            if hasattr(self.core, "fetch_rows"):  # download the band, not the neighbours' halo rows
+                img, err = self.core.fetch_rows(lo, hi)
+            else:
+                slab_img, err = self.core.fetch()
+                img = slab_img[lo:hi]
         total = torch.tensor(np.asarray(err, np.float64), device=self._reduce_device())
         self.dist.all_reduce(total, group=self.group)
         return img, total.cpu().numpy().astype(np.float32)
@@ -422,6 +425,9 @@ class CudaBandCore:
 
     def fetch(self):
         return self.solver.fetch()
+
+    def fetch_rows(self, lo, hi, img=None):
+        return self.solver.fetch_rows(lo, hi, img)
 
     def state(self):
         return self.solver.state()

@@ -16,10 +16,12 @@ include/fpie_b200.h).
 
 from __future__ import annotations
 
+import sys
 import threading
 
 import numpy as np
 
+from . import _lib
 from .solver import EquSolver, GridSolver
 
 BACKEND = "b200"
@@ -40,6 +42,12 @@ class BaseProcessor:
         self.rank = 0
         self.root = True
         self.tgt = None
+        self.box = None
+        self._canvas = None
+
+    def _require_reset(self) -> None:
+        if self.tgt is None or self.box is None:  # the same error the core raises (GridSolver::require_ready)
+            raise RuntimeError(f"{type(self).__name__}: step called before reset")
 
     def sync(self) -> None:
         self.core.sync()
@@ -54,7 +62,20 @@ class BaseProcessor:
     def _reset_with_canvas(self, tgt, device_reset):
         """Run the device-side reset while a worker thread makes the Processor's private copy of
         the target (process.py:268 / 384); both release the GIL, so they overlap."""
-        canvas = np.empty(tgt.shape, np.uint8)
+        # page-locked, so that every step's device-to-host copy of the result runs at PCIe speed.  The
+        # reference hands out a fresh copy per reset (`tgt.copy()`); page-locking is too slow for that, so
+        # the previous canvas is recycled -- but only when nobody outside this object can still see it
+        # (the GUI's reset + step per click, fpie/gui.py:96-99, drops the old image first)
+        canvas = None
+        if self._canvas is not None and self._canvas.shape == tgt.shape:
+            self.tgt = None
+            base = self._canvas.base
+            # references: self._canvas + getrefcount's argument; base: the canvas + `base` + the argument
+            if sys.getrefcount(self._canvas) <= 2 and (base is None or sys.getrefcount(base) <= 3):
+                canvas = self._canvas
+            del base
+        if canvas is None:
+            canvas = self._canvas = _lib.pinned_empty(tgt.shape, np.uint8)
         rows = tgt.shape[0]
         parts = 4 if tgt.size >= (8 << 20) else 1  # large images: fault the fresh pages in from several threads
         bounds = [rows * i // parts for i in range(parts + 1)]
@@ -100,6 +121,7 @@ class EquProcessor(BaseProcessor):
     def step(self, iteration: int):
         # process.py:278 `self.tgt[self.tgt_index] = x[1:]`: the device scatters the K solved pixels into
         # its copy of the crop, the device-to-host copy lands it in self.tgt[x0:x1, y0:y1]
+        self._require_reset()
         x0, _, y0, _ = self.box
         err = self.core.step_paste_into(iteration, self.tgt, x0, y0)
         return self.tgt, err
@@ -118,11 +140,13 @@ class GridProcessor(BaseProcessor):
         self._check_images(src, mask, tgt)
         n, box = self._reset_with_canvas(
             tgt, lambda: self.core.reset_from_images(src, mask, tgt, mask_on_src, mask_on_tgt, self.gradient))
+        self.box = box
         self.x0, self.x1, self.y0, self.y1 = box
         return n
 
     def step(self, iteration: int):
         # process.py:393 `self.tgt[x0:x1, y0:y1] = tgt`, done by the device-to-host copy itself
+        self._require_reset()
         err = self.core.step_into(iteration, self.tgt, self.x0, self.y0)
         return self.tgt, err
 

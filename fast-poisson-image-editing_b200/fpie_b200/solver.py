@@ -34,15 +34,28 @@ def _mask_view(mask) -> np.ndarray:
     return m
 
 
+def _as_u8(arr, what: str) -> np.ndarray:
+    """uint8 passes through; any other dtype must already hold whole numbers in 0..255 (the reference
+    does its arithmetic in float32 on whatever it is given, fpie/process.py:227-246 -- values that a
+    uint8 cannot hold would silently wrap here, so they are rejected instead)."""
+    a = np.asarray(arr)
+    if a.dtype != np.uint8:
+        if a.dtype == np.bool_ or not (np.issubdtype(a.dtype, np.integer) or np.issubdtype(a.dtype, np.floating)):
+            raise ValueError(f"{what} must be a uint8 array (got {a.dtype}); scale boolean / normalised data to 0..255")
+        if a.size and (a.min() < 0 or a.max() > 255 or (np.issubdtype(a.dtype, np.floating) and np.any(a != np.rint(a)))):
+            raise ValueError(f"{what} must hold whole numbers in 0..255 to be taken as uint8 (got {a.dtype} outside that set)")
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
 def _as_u8_image(img, what: str) -> np.ndarray:
-    a = np.ascontiguousarray(img, dtype=np.uint8)
+    a = _as_u8(img, what)
     if a.ndim != 3 or a.shape[2] != 3:
         raise ValueError(f"{what} must be a uint8 [rows, cols, 3] image")
     return a
 
 
 def _as_u8_mask(mask) -> np.ndarray:
-    a = np.ascontiguousarray(mask, dtype=np.uint8)
+    a = _as_u8(mask, "mask")
     if a.ndim == 2:
         return a[:, :, None]
     if a.ndim == 3 and 1 <= a.shape[2] <= 16:
@@ -87,8 +100,10 @@ class GridSolver(_Handle):
         self.grid_x, self.grid_y = int(grid_x), int(grid_y)
         self.device = default_device() if device is None else int(device)
         self.shape = None
-        stream = _lib.current_stream_handle(self.device)
-        self.stream_handle = stream  # the torch stream that was current at construction
+        # the torch stream that was current at construction; the Stream object is kept alive with the solver
+        # (a collected torch stream would leave the core holding a dangling cudaStream_t)
+        self._stream_owner, stream = _lib.current_stream(self.device)
+        self.stream_handle = stream
         _lib.check(self._lib.fpie_b200_grid_create(self.device, ctypes.c_void_p(stream), int(block_k), int(variant),
                                                    ctypes.byref(self._h)))
 
@@ -263,6 +278,18 @@ class GridSolver(_Handle):
         _lib.check(self._lib.fpie_b200_grid_fetch(self.handle, _ptr(img, ctypes.c_uint8), _ptr(err, ctypes.c_float)))
         return img, err
 
+    def fetch_rows(self, lo: int, hi: int, img: np.ndarray | None = None):
+        """``fetch`` of rows ``[lo, hi)`` only (a row band's own rows, without its halo rows)."""
+        n, w = self._need_shape()
+        if not 0 <= lo <= hi <= n:
+            raise ValueError("row range outside the grid")
+        if img is None:
+            img = np.empty((hi - lo, w, 3), np.uint8)
+        err = np.empty(3, np.float32)
+        _lib.check(self._lib.fpie_b200_grid_fetch_rows(self.handle, int(lo), int(hi), _ptr(img, ctypes.c_uint8),
+                                                       _ptr(err, ctypes.c_float)))
+        return img, err
+
     def info(self) -> dict:
         unk, launches, act, tot = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
         k = ctypes.c_int()
@@ -318,7 +345,8 @@ class EquSolver(_Handle):
         self.mode = mode
         self.N = 0
         self.crop_shape = None
-        stream = _lib.current_stream_handle(self.device)
+        self._stream_owner, stream = _lib.current_stream(self.device)
+        self.stream_handle = stream
         _lib.check(self._lib.fpie_b200_equ_create(self.device, ctypes.c_void_p(stream), int(block_size),
                                                   ctypes.byref(self._h)))
         if mode != "jacobi":

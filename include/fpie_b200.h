@@ -55,6 +55,13 @@ int fpie_b200_device_count(void);
  * fpie/core/cuda/utils.cu:5-22; here it is a query, not a side effect). */
 int fpie_b200_device_info(int device, char *name, int name_len, int *sm_count, int *cc_major, int *cc_minor);
 
+/* Page-locked host memory for the images that cross the boundary: a `step` that lands its uint8
+ * result in pinned memory runs at PCIe speed, a pageable destination costs several times that
+ * (the reference returns a fresh pageable numpy array from every step, fpie/core/cuda/grid.cu:152).
+ * The Processor layer keeps its full-size target canvas (fpie/process.py:268, 384) in such a buffer. */
+int fpie_b200_host_alloc(int64_t bytes, void **out);
+int fpie_b200_host_free(void *ptr);
+
 /* ---- GridSolver ---------------------------------------------------------
  * Replaces CudaGridSolver (fpie/core/cuda/grid.cu:7-153) behind the
  * GridSolver interface of fpie/core/base_solver.h:77-152. */
@@ -108,6 +115,10 @@ int fpie_b200_grid_sweeps_async(fpie_b200_grid *g, int iters);
 int fpie_b200_grid_finish_async(fpie_b200_grid *g);
 int fpie_b200_grid_sync(fpie_b200_grid *g);
 int fpie_b200_grid_fetch(fpie_b200_grid *g, uint8_t *out_img, float *out_err3);
+/* fetch() of rows [row_lo, row_hi) only -> out_img [row_hi - row_lo, m, 3]: a row band downloads its own
+ * rows, not the halo rows it holds of its neighbours (the reference's MPI GridSolver gathers exactly the
+ * band rows on the root, fpie/core/mpi/grid.cc:137-146). */
+int fpie_b200_grid_fetch_rows(fpie_b200_grid *g, int row_lo, int row_hi, uint8_t *out_img, float *out_err3);
 
 /* Number of masked pixels (unknowns) and kernel launches issued so far. */
 int fpie_b200_grid_info(fpie_b200_grid *g, int64_t *unknowns, int64_t *launches, int *block_k,
