@@ -67,21 +67,6 @@ def profiled_traffic(kernel: str):
         return None
 
 
-def scaling_reference(name: str):
-    """The single-GPU figure of the multi-GPU workload, from the committed scaling record (the N = 1 run of
-    this script measures the headline workload, config 2, not config 4).  None when no record exists."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_scaling_cfg4.json")) as f:
-            rec = json.load(f)
-        if not rec.get("workload", "").startswith(name):
-            return None
-        one = next(r for r in rec["runs"] if r["n_gpus"] == 1)
-        return {"n_gpus": 1, "workload": rec["workload"], "value": one["gupd_per_s"], "unit": "Gupd/s",
-                "source": "profiles/r01_scaling_cfg4.json (python bench.py --workload cfg4)"}
-    except Exception:
-        return None
-
-
 class ClockSampler:
     """Samples SM clocks and throttle reasons with NVML while the timed region runs."""
 
@@ -431,31 +416,128 @@ def run_single(args, work, name):
     print(json.dumps(line))
 
 
-def slab_images(work, plan, n, m, rank):
-    """Synthetic uint8 slab (rows plan.slab_lo:plan.slab_hi of an n x m blend)."""
+CHUNK_ROWS = 1024
+
+
+def global_rows(kind: str, lo: int, hi: int, m: int, seed: int = 0) -> np.ndarray:
+    """Rows [lo, hi) of the ONE synthetic image `kind` ("src" / "tgt") of a row-band sharded problem.  Every
+    chunk of CHUNK_ROWS rows is drawn from its own generator seeded by (seed, kind, chunk index), so any rank
+    reproduces any row range of the same global image: neighbouring slabs agree on the rows they share."""
+    out = np.empty((hi - lo, m, 3), np.uint8)
+    tag = {"src": 1, "tgt": 2}[kind]
+    for c in range(lo // CHUNK_ROWS, (hi + CHUNK_ROWS - 1) // CHUNK_ROWS):
+        r0 = c * CHUNK_ROWS
+        chunk = np.random.default_rng([seed, tag, c]).integers(0, 256, size=(CHUNK_ROWS, m, 3), dtype=np.uint8)
+        a, b = max(lo, r0), min(hi, r0 + CHUNK_ROWS)
+        out[a - lo : b - lo] = chunk[a - r0 : b - r0]
+    return out
+
+
+def slab_images(work, lo, hi, n, m):
+    """uint8 rows [lo, hi) of the global n x m blend (src, canonical crop mask, tgt) and its unknown count."""
     from fpie_b200 import synth
 
-    rows = plan.slab_rows
-    rng = np.random.default_rng(1000 + rank)
-    src = np.empty((rows, m, 3), np.uint8)
-    tgt = np.empty((rows, m, 3), np.uint8)
-    for img in (src, tgt):
-        for r in range(0, rows, 2048):
-            img[r : r + 2048] = rng.integers(0, 256, size=(min(2048, rows - r), m, 3), dtype=np.uint8)
+    src = global_rows("src", lo, hi, m)
+    tgt = global_rows("tgt", lo, hi, m)
     if work["mask"] == "square":
-        mask = np.full((rows, m), 255, np.uint8)
+        mask = np.full((hi - lo, m), 255, np.uint8)
+        mask[:, 0] = mask[:, -1] = 0
+        if lo == 0:
+            mask[0] = 0
+        if hi == n:
+            mask[-1] = 0
         unknowns = (n - 2) * (m - 2)
     else:
         full = synth.make_mask(work["mask"], n, m)
         full[0] = full[-1] = 0
         full[:, 0] = full[:, -1] = 0
-        mask = np.ascontiguousarray(full[plan.slab_lo : plan.slab_hi])
+        mask = np.ascontiguousarray(full[lo:hi])
         unknowns = int((full > 127).sum())
     return src, mask, tgt, unknowns
 
 
+def band_parity_check(work, world, rank, dev, dist, halo, block_k, overlap, transport):
+    """The shipped multi-GPU path against one GPU, in the same run: a reduced problem of the same kind
+    (world bands of 1024 x 8192 pixels, 96 sweeps = 4 halo exchanges) is solved by the row-band solver over the
+    same transport as the timed run, and -- independently, on every rank's own GPU -- as one unsharded grid.
+    Each rank compares its band of the fp32 state bit for bit; err must agree to 1e-4 relative."""
+    import torch
+
+    import fpie_b200
+    from fpie_b200 import band
+
+    m, rows_per_band, sweeps = 8192, 1024, 96
+    n = rows_per_band * world
+    plan = band.make_plan(n, world, rank, halo)
+    src, mask, tgt, unknowns = slab_images(work, plan.slab_lo, plan.slab_hi, n, m)
+    core = fpie_b200.GridSolver(8, 8, device=dev, block_k=block_k)
+    solver = band.make_band_solver(core, dist, halo=halo, overlap=overlap, transport=transport)
+    solver.reset_slab(n, src, mask, tgt, work["grad"])
+    band_img, err = solver.step(sweeps)
+    band_state = solver.band_state()
+    exchanges = solver.exchanges_done if hasattr(solver, "exchanges_done") else None
+    solver.close()
+    core.close()
+    # the same problem on this rank's GPU alone
+    fsrc, fmask, ftgt, _ = slab_images(work, 0, n, n, m)
+    one = fpie_b200.GridSolver(8, 8, device=dev, block_k=block_k)
+    one.reset_slab(fsrc, fmask, ftgt, work["grad"])
+    img1, err1 = one.step(sweeps)
+    state1 = one.state()[plan.band_lo : plan.band_hi]
+    one.close()
+    ok_state = bool(np.array_equal(band_state.view(np.uint32), state1.view(np.uint32)))
+    ok_img = bool(np.array_equal(band_img, img1[plan.band_lo : plan.band_hi]))
+    err_rel = float(np.max(np.abs(err.astype(np.float64) - err1) / np.maximum(np.abs(err1), 1e-30)))
+    flags = torch.tensor([int(ok_state), int(ok_img)], device="cuda")
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    worst = torch.tensor([err_rel], device="cuda", dtype=torch.float64)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    return {
+        "state_bit_exact": bool(flags[0].item()),
+        "u8_equal": bool(flags[1].item()),
+        "err_rel": float(worst.item()),
+        "err_tol": 1e-4,
+        "problem": f"{n}x{m} {work['mask']} mask, {world} bands, {sweeps} sweeps, halo {halo}, vs one unsharded GPU "
+                   f"solve of the same images on every rank",
+        "exchanges": exchanges,
+        "unknowns": unknowns,
+    }
+
+
+def single_gpu_reference(work, n, m, iters, dev, block_k, steps=1):
+    """The multi-GPU workload on ONE GPU, measured in the same run (rank 0, the other ranks wait): what
+    strong-scaling efficiency is computed against."""
+    import torch
+
+    import fpie_b200
+
+    src, mask, tgt, unknowns = slab_images(work, 0, n, n, m)
+    core = fpie_b200.GridSolver(8, 8, device=dev, block_k=block_k)
+    core.reset_slab(src, mask, tgt, work["grad"])
+    del src, mask, tgt
+    info = core.info()
+    k = info["block_k"]
+    core.sweeps_async(20 * k)
+    core.finish_async()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms = []
+    for _ in range(steps):
+        e0.record()
+        core.sweeps_async(iters)
+        core.finish_async()
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    core.close()
+    t = float(np.mean(ms))
+    return {"n_gpus": 1, "value": unknowns * iters / (t * 1e-3) / 1e9, "unit": "Gupd/s", "ms_per_step": t,
+            "steps": steps, "block_k": k, "variant": info["variant"],
+            "source": "measured in this run on rank 0's GPU (same images, same sweeps, no sharding)"}
+
+
 def run_band(args, work, name):
-    """N > 1: the grid is cut into row bands, one process per GPU, deep halos over NCCL."""
+    """N > 1: the grid is cut into row bands, one process per GPU, deep halos between neighbours."""
     import torch
 
     import fpie_b200
@@ -469,9 +551,9 @@ def run_band(args, work, name):
     iters = args.iters or work["iters"]
     halo = args.halo
     plan = band.make_plan(n, world, rank, halo)
-    src, mask, tgt, unknowns = slab_images(work, plan, n, m, rank)
+    src, mask, tgt, unknowns = slab_images(work, plan.slab_lo, plan.slab_hi, n, m)
     core = fpie_b200.GridSolver(8, 8, device=dev, block_k=args.block_k)
-    solver = band.BandGridSolver(band.CudaBandCore(core), dist, halo=halo, overlap=not args.no_overlap)
+    solver = band.make_band_solver(core, dist, halo=halo, overlap=not args.no_overlap, transport=args.transport)
     t0 = time.perf_counter()
     solver.reset_slab(n, src, mask, tgt, work["grad"])
     torch.cuda.synchronize()
@@ -505,25 +587,52 @@ def run_band(args, work, name):
 
     # end to end: every rank uploads its uint8 slab from pinned memory, solves, downloads its band
     psrc, pmask, ptgt = pinned_copy(src), pinned_copy(mask), pinned_copy(tgt)
-    e2e_t = []
+    del src, mask, tgt
+    e2e_t, e2e_reset = [], []
     for i in range(3):
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
         solver.reset_slab(n, psrc, pmask, ptgt, work["grad"])
+        t1 = time.perf_counter()
         img, err = solver.step(iters)
         torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], device="cuda")
+        dt = torch.tensor([time.perf_counter() - t0, t1 - t0], device="cuda")
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         if i:
-            e2e_t.append(float(dt.item()))
+            e2e_t.append(float(dt[0].item()))
+            e2e_reset.append(float(dt[1].item()))
     e2e_s = float(np.mean(e2e_t))
-    h2d = torch.tensor([src.nbytes + mask.nbytes + tgt.nbytes], device="cuda", dtype=torch.float64)
-    d2h = torch.tensor([plan.slab_rows * m * 3 + 12], device="cuda", dtype=torch.float64)
+    h2d = torch.tensor([psrc.nbytes + pmask.nbytes + ptgt.nbytes], device="cuda", dtype=torch.float64)
+    d2h = torch.tensor([(plan.band_hi - plan.band_lo) * m * 3 + 12], device="cuda", dtype=torch.float64)
     dist.all_reduce(h2d)
     dist.all_reduce(d2h)
-
     info = core.info()
+    exchange_desc = solver.describe() if hasattr(solver, "describe") else "NCCL send/recv"
+    solver.close()
+    core.close()
+    del psrc, pmask, ptgt, img
+    _PINNED.clear()
+    torch.cuda.empty_cache()
+
+    # correctness of exactly this path, in this run (all ranks)
+    parity = None
+    if not args.no_parity:
+        parity = band_parity_check(work, world, rank, dev, dist, halo, args.block_k, not args.no_overlap, args.transport)
+    # the same workload on one GPU, in this run (rank 0; the others wait at the barrier)
+    ref1 = None
+    if rank == 0 and not args.no_scaling_reference:
+        ref1 = single_gpu_reference(work, n, m, iters, dev, args.block_k)
+    dist.barrier()
+    base = None
+    if rank == 0 and not args.no_cpu_baseline:
+        # the reference's OpenMP core overflows int32 offsets at 3*N*M >= 2^31 (base_solver.h:114-117): the host
+        # baseline runs the same kind of problem at 8192^2 (per-pixel throughput is size-independent there)
+        w8 = dict(work, size=8192)
+        s8, m8, t8, _ = slab_images(w8, 0, 8192, 8192, 8192)
+        base, _, _, _ = cpu_baseline(w8, s8, m8, t8, budget_s=args.cpu_budget)
+        base["sample"] += " -- 8192^2 instead of 32768^2: the reference core cannot index the full problem"
+
     k = info["block_k"]
     peak, peak_src = measured_peak()
     # per-GPU roofline of the sweep kernel on this rank's slab (rank 0 reports)
@@ -541,34 +650,43 @@ def run_band(args, work, name):
             "higher_is_better": True,
             "scaling": "strong",
             # strong scaling of ONE fixed problem; its single-GPU figure is not what `--gpus 1` runs (config 2)
-            "scaling_reference": scaling_reference(name) if not (args.size or args.iters) else None,
+            "scaling_reference": ref1,
+            "scaling_efficiency_vs_reference": (value / (world * ref1["value"])) if ref1 else None,
+            "parity": parity,
             "vs_baseline": None,
             "dtype": "f32",
             "data": "synthetic",
             "config": {
                 "workload": f"{name}: grid solver, {n}x{m}x3 {work['mask']} mask, grad {work['grad']}, {iters} sweeps per "
-                f"step, {world} row bands, halo {halo} rows exchanged every {halo} sweeps (NCCL send/recv)",
+                f"step, {world} row bands, halo {halo} rows exchanged every {halo} sweeps ({exchange_desc})",
                 "unknowns": unknowns,
                 "sweeps_per_step": iters,
                 "block_k": k,
                 "halo": halo,
-                "exchange": "overlapped with the interior tiles of a pass (second stream)" if solver.exchange_overlaps
-                else "between passes",
+                "transport": args.transport,
+                "exchange": exchange_desc,
                 "band_rows": plan.band_hi - plan.band_lo,
                 "l2": "per-GPU slab far exceeds the 126 MB L2; no flush needed",
                 "reset_s": reset_s,
+                "images": "one global image pair, generated per row chunk from (seed, chunk) so that neighbouring slabs "
+                          "hold identical rows: the sharded solve is the single-GPU solve",
             },
             "roofline": {
                 "bound": "hbm", "kernel": "grid_sweepk_pipe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,  # (the ncu capture is of config 2 on one GPU)
+                "frac": achieved / peak,
+                "traffic": profiled_traffic("grid_sweepk_pipe_kernel_band_k12"),
                 "peak_source": peak_src,
                 "note": "per-GPU effective bandwidth (36 B x unknowns of one band x sweeps / step time, halo "
-                        "exchange and epilogue included)",
+                        "exchange and epilogue included); traffic = DRAM bytes of one 12-sweep pass over one of 8 bands "
+                        "(ncu, one GPU, profiles/)",
             },
-            "cpu_baseline": None,
+            "cpu_baseline": base,
             "e2e": {"value": unknowns * iters / e2e_s / 1e9, "unit": "Gupd/s", "h2d_bytes_per_step": int(h2d.item()),
                     "d2h_bytes_per_step": int(d2h.item()), "ms_per_step": e2e_s * 1e3,
-                    "api": "BandGridSolver.reset_slab(uint8 slabs) + step() per rank, pinned host buffers"},
+                    "reset_ms": float(np.mean(e2e_reset)) * 1e3,
+                    "h2d_gbs_per_gpu": float(h2d.item()) / world / max(float(np.mean(e2e_reset)), 1e-9) / 1e9,
+                    "api": "BandGridSolver.reset_slab(uint8 slabs) + step() per rank, pinned host buffers; the band "
+                           "rows only come back"},
             "gpu_launches": int(launches.item()),
             "clocks": clocks.summary(),
         }
@@ -593,6 +711,11 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--equ-mode", default="gather", choices=["gather", "jacobi", "redblack"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
+                    help="row bands: halo rows by copy-engine peer copies behind the C ABI (p2p) or NCCL send/recv")
+    ap.add_argument("--no-parity", action="store_true", help="row bands: skip the in-run sharded-vs-single-GPU check")
+    ap.add_argument("--no-scaling-reference", action="store_true",
+                    help="row bands: skip the in-run single-GPU measurement of the same workload")
     args = ap.parse_args()
     name = args.workload or ("cfg2" if args.gpus == 1 else "cfg4")
     work = WORKLOADS[name]

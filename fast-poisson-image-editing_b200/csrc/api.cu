@@ -123,6 +123,46 @@ API int fpie_b200_grid_flip(fpie_b200_grid *g) {
   NEED(g);
   return guarded([&] { g->impl.flip(); });
 }
+API int fpie_b200_grid_halo_config(fpie_b200_grid *g, int band_lo, int band_hi, int force_rebuild, int *changed) {
+  NEED(g);
+  return guarded([&] {
+    const bool c = g->impl.halo_config(band_lo, band_hi, force_rebuild != 0);
+    if (changed) *changed = c ? 1 : 0;
+  });
+}
+API int fpie_b200_grid_halo_export(fpie_b200_grid *g, int side, unsigned char *blob) {
+  NEED(g);
+  return guarded([&] { g->impl.halo_export(side, blob); });
+}
+API int fpie_b200_grid_halo_connect(fpie_b200_grid *g, int side, const unsigned char *blob, int same_process) {
+  NEED(g);
+  return guarded([&] { g->impl.halo_connect(side, blob, same_process != 0); });
+}
+API int fpie_b200_grid_band_sweeps_async(fpie_b200_grid *g, int iters) {
+  NEED(g);
+  return guarded([&] { g->impl.band_sweeps_async(iters); });
+}
+API int fpie_b200_grid_halo_stats(fpie_b200_grid *g, int64_t *exchanges) {
+  NEED(g);
+  return guarded([&] {
+    if (exchanges) *exchanges = g->impl.halo_exchanges();
+  });
+}
+API int fpie_b200_grid_halo_debug(fpie_b200_grid *g, int64_t *out16) {
+  NEED(g);
+  return guarded([&] { g->impl.halo_debug(out16); });
+}
+API int fpie_b200_grid_halo_trace_begin(fpie_b200_grid *g, int max_intervals) {
+  NEED(g);
+  return guarded([&] { g->impl.halo_trace_begin(max_intervals); });
+}
+API int fpie_b200_grid_halo_trace_read(fpie_b200_grid *g, float *out, int max_floats, int *written) {
+  NEED(g);
+  return guarded([&] {
+    const int n = g->impl.halo_trace_read(out, max_floats);
+    if (written) *written = n;
+  });
+}
 API int fpie_b200_grid_set_formulation(fpie_b200_grid *g, int equ) {
   NEED(g);
   return guarded([&] { g->impl.set_formulation(equ != 0); });

@@ -716,6 +716,7 @@ GridSolver::GridSolver(int device, cudaStream_t stream, int block_k, int variant
 GridSolver::~GridSolver() {
   // (runs from Python's garbage collector on whatever thread and current device it happens to be:
   // restore the caller's device; no exceptions out of a destructor, hence no DeviceGuard)
+  halo_disconnect();
   int prev = -1;
   cudaGetDevice(&prev);
   cudaSetDevice(device_);
@@ -1102,10 +1103,16 @@ struct SweepArgs {
   bool h16;
   int reverse;  // walk the tile list backwards (alternate passes: L2 reuse of the previous pass's last tiles)
   int ntiles, nsweeps, halo_y, halo_x;
+  bool load_only;  // resolve (load) the kernel and set its attributes, launch nothing
 };
 
 template <int R, int NW>
 void launch_direct(const SweepArgs &a) {
+  if (a.load_only) {
+    cudaFuncAttributes attr;
+    CUDA_CHECK(cudaFuncGetAttributes(&attr, grid_sweepk_kernel<R, NW>));
+    return;
+  }
   grid_sweepk_kernel<R, NW><<<std::min(a.ntiles, a.grid), NW * 32, 0, a.stream>>>(a.g, a.bits, a.xin, a.xout, a.hq, a.tiles, a.ntiles,
                                                               a.nsweeps, a.halo_y, a.halo_x);
 }
@@ -1121,6 +1128,7 @@ void launch_pipe_h(const SweepArgs &a) {
     CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured_device = dev;
   }
+  if (a.load_only) return;
   const int grid = std::min(a.ntiles, a.grid * OCC);
   // programmatic dependent launch: the next pass may be scheduled while this one drains; its CTAs run
   // their prologue (barrier init, descriptor fetch) and block in griddepcontrol.wait until this grid
@@ -1159,6 +1167,7 @@ void launch_pair_h(const SweepArgs &a) {
     CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured_device = dev;
   }
+  if (a.load_only) return;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(std::min(a.ntiles, a.grid * OCC));
   cfg.blockDim = dim3(NW * 32);
@@ -1415,7 +1424,32 @@ void GridSolver::pass_async(int nsweeps, int part) {
   FPIE_REQUIRE(edge_rows_ > 0, "pass_async needs set_edge_rows");
   FPIE_REQUIRE(variant_ != 1, "pass_async: not available for the one-sweep-per-launch kernels");
   DeviceGuard guard(device_);
-  if (stats_.unknowns == 0 || n_part_[part] == 0) return;
+  run_pass(nsweeps, tiles_part_[part].ptr, n_part_[part]);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// CUDA loads kernels lazily, at their first launch, and loading may synchronise the whole context.  A band
+// whose stream already waits for a neighbour's rows must never trigger that (several bands of one process
+// would deadlock: the load waits for the stream, the stream for a band that cannot launch), so everything a
+// step launches is resolved up front.
+void GridSolver::preload_kernels() {
+  DeviceGuard guard(device_);
+  cudaFuncAttributes attr;
+  CUDA_CHECK(cudaFuncGetAttributes(&attr, grid_residual_kernel));
+  CUDA_CHECK(cudaFuncGetAttributes(&attr, grid_to_u8_kernel));
+  CUDA_CHECK(cudaFuncGetAttributes(&attr, planes_to_aos_kernel));
+  CUDA_CHECK(cudaFuncGetAttributes(&attr, grid_sweep1_kernel));
+  if (variant_ != 1) {
+    SweepArgs a{};
+    a.load_only = true;
+    a.h16 = h16_ok_;
+    launch_variant(variant_, a);
+  }
+}
+
+// one pass (<= block_k sweeps) over the tiles of `tiles`, current buffer -> other buffer, no flip
+void GridSolver::run_pass(int nsweeps, const int2 *tiles, int ntiles) {
+  if (stats_.unknowns == 0 || ntiles == 0) return;
   SweepArgs a{};
   a.grid = sm_count_;
   a.stream = stream_;
@@ -1425,8 +1459,8 @@ void GridSolver::pass_async(int nsweeps, int part) {
   a.h16 = h16_ok_;
   a.tm_h = h16_ok_ ? &tm_h16_ : &tm_h_;
   a.tm_m = &tm_m_;
-  a.tiles = tiles_part_[part].ptr;
-  a.ntiles = n_part_[part];
+  a.tiles = tiles;
+  a.ntiles = ntiles;
   a.halo_y = block_k_;
   a.halo_x = halo_x_;
   a.nsweeps = nsweeps;
@@ -1435,7 +1469,6 @@ void GridSolver::pass_async(int nsweeps, int part) {
   a.tm_x = &tm_x_[cur_];
   launch_variant(variant_, a);
   stats_.launches += 1;
-  CUDA_CHECK(cudaGetLastError());
 }
 
 void GridSolver::flip() {

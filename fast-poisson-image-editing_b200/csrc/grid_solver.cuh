@@ -75,6 +75,23 @@ class GridSolver {
   void set_formulation(bool equ) { equ_form_ = equ; }
   void band_view(int which, float **base, int64_t *plane_stride, int64_t *row_pitch, int *pad_rows, int *pad_cols);
 
+  // ---- row-band halo link: peer copies + stream memory operations behind the C ABI (halo.cu) ----
+  static constexpr int kHaloBlobBytes = 128;
+  // this slab holds grid rows [band_lo, band_hi) of its own plus the rows above / below them as halos
+  bool halo_config(int band_lo, int band_hi, bool force = false);  // true when the link was (re)built: export / connect again
+  // receive box of side (0 = up, 1 = down) as an opaque blob for the neighbour on that side
+  void halo_export(int side, unsigned char *blob);
+  // the neighbour's receive box for MY rows; same_process: the blob carries a raw pointer, not an IPC handle
+  void halo_connect(int side, const unsigned char *blob, bool same_process);
+  void halo_disconnect();
+  // `iters` sweeps; halo rows refreshed every `halo` sweeps (halo = rows held of each neighbour)
+  void band_sweeps_async(int iters);
+  int64_t halo_exchanges() const { return halo_exchanges_; }
+  void halo_debug(int64_t *out16);
+  // phase trace of the first intervals of the next band_sweeps_async call (milliseconds since its start)
+  void halo_trace_begin(int max_intervals);
+  int halo_trace_read(float *out, int max_floats);
+
   int device() const { return device_; }
   int block_k() const { return block_k_; }
   int current() const { return cur_; }
@@ -144,6 +161,33 @@ class GridSolver {
   int n_tile_entries_ = 0;
   double *host_err_ = nullptr;  // pinned [4]
   GridStats stats_;
+
+  struct HaloSide {
+    int rows = 0;                       // halo rows held on this side (0 = no neighbour)
+    int row_send = 0, row_recv = 0;     // first grid row sent to / refreshed from the neighbour
+    unsigned char *inbox = nullptr;     // device: [2 parities][3 planes][rows][m] floats, then 2 flag words
+    size_t inbox_bytes = 0, parity_bytes = 0;
+    unsigned char *remote = nullptr;    // the neighbour's inbox for MY rows, mapped into this process
+    bool remote_ipc = false;
+    uint32_t sent = 0, received = 0;    // exchange intervals so far (the flag words carry these counters)
+  };
+  void halo_free_side(HaloSide &s);
+  void halo_send(int which);
+  void halo_recv(int which);
+  void run_pass(int nsweeps, const int2 *tiles, int ntiles);
+  void preload_kernels();
+  HaloSide halo_[2];
+  int band_lo_ = 0, band_hi_ = 0;
+  bool halo_pending_ = false;
+  int64_t halo_exchanges_ = 0;
+  cudaStream_t halo_stream_ = nullptr;
+  cudaEvent_t ev_edge_ = nullptr, ev_sent_ = nullptr;
+  uint32_t *halo_seq_ = nullptr;  // device: [2] flag values in flight (source of the 4-byte flag copies)
+  // trace
+  std::vector<cudaEvent_t> trace_ev_;
+  std::vector<int> trace_tag_;
+  int trace_left_ = 0;
+  void trace_mark(int tag, cudaStream_t s);
 };
 
 }  // namespace fpie

@@ -19,7 +19,7 @@ INCLUDE = os.path.join(REPO_ROOT, "include")
 LIB_PATH = os.path.join(PKG_DIR, "libfpie_b200.so")
 OBJ_DIR = os.path.join(DIST_ROOT, "build")
 
-SOURCES = ("api.cu", "grid.cu", "equ.cu", "prep.cu")
+SOURCES = ("api.cu", "grid.cu", "halo.cu", "equ.cu", "prep.cu")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # -fmad=false: every fused multiply-add in the kernels is an explicit intrinsic;
 # nothing else may be contracted, or fp32 results drift from the reference's.
@@ -42,6 +42,9 @@ def _stale(target: str, deps) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, defines=(), lib_path: str = LIB_PATH, obj_dir: str = OBJ_DIR) -> str:
+    # FPIE_B200_ALL_VARIANTS=1: also compile the measured-and-dominated tile shapes (tuning / full test builds)
+    if os.environ.get("FPIE_B200_ALL_VARIANTS", "") not in ("", "0") and "FPIE_ALL_VARIANTS" not in defines:
+        defines = (*defines, "FPIE_ALL_VARIANTS")
     os.makedirs(obj_dir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(INCLUDE, "fpie_b200.h"))

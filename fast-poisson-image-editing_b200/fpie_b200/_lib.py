@@ -44,6 +44,14 @@ SIGNATURES = {
     "fpie_b200_grid_sync": [c_void_p],
     "fpie_b200_grid_fetch": [c_void_p, u8p, f32p],
     "fpie_b200_grid_fetch_rows": [c_void_p, c_int, c_int, u8p, f32p],
+    "fpie_b200_grid_halo_config": [c_void_p, c_int, c_int, c_int, intp],
+    "fpie_b200_grid_halo_export": [c_void_p, c_int, u8p],
+    "fpie_b200_grid_halo_connect": [c_void_p, c_int, u8p, c_int],
+    "fpie_b200_grid_band_sweeps_async": [c_void_p, c_int],
+    "fpie_b200_grid_halo_stats": [c_void_p, i64p],
+    "fpie_b200_grid_halo_debug": [c_void_p, i64p],
+    "fpie_b200_grid_halo_trace_begin": [c_void_p, c_int],
+    "fpie_b200_grid_halo_trace_read": [c_void_p, f32p, c_int, intp],
     "fpie_b200_grid_info": [c_void_p, i64p, i64p, intp, i64p, i64p],
     "fpie_b200_grid_reset_from_images": [c_void_p, u8p, c_int, c_int, u8p, c_int, c_int, c_int, u8p, c_int, c_int,
                                          c_int, c_int, c_int, c_int, c_int, i64p, i32p],

@@ -268,6 +268,123 @@ class BandGridSolver:
         return getattr(self.core, "torch_device", "cpu")
 
 
+class P2PBandGridSolver(BandGridSolver):
+    """``BandGridSolver`` whose halo exchange runs behind the C ABI (``csrc/halo.cu``): copy-engine peer
+    copies over NVLink into the neighbour's receive box, flag words and stream-level waits instead of
+    NCCL send/recv kernels, and the whole per-interval schedule (edge tiles, exchange, interior tiles)
+    issued by one C call per ``sweeps``.  ``torch.distributed`` is the control plane only: the
+    128-byte link descriptors at (re)connection, the barrier of ``sync`` and the 3-float ``err`` sum --
+    so the group may be NCCL (one process per GPU) or gloo (CPU tensors; several processes sharing one
+    GPU in the tests).  ``same_process=True``: the neighbours are solvers of this very process (threads),
+    linked by raw device pointers instead of CUDA IPC handles.
+
+    Needs every band to be non-empty (bands >= halo rows); ``make_band_solver`` falls back to the NCCL
+    transport otherwise."""
+
+    def __init__(self, core, dist, group=None, halo: int = 24, overlap: bool = True, same_process: bool = False):
+        super().__init__(core, dist, group, halo, overlap)
+        self.same_process = bool(same_process)
+        self._split = False
+        self.exchanges_done = 0
+
+    @property
+    def exchange_overlaps(self) -> bool:
+        return self.plan is not None and (self.plan.up is not None or self.plan.down is not None)
+
+    def describe(self) -> str:
+        return ("copy-engine peer copies + stream memory operations behind the C ABI, overlapped with the interior "
+                "tiles of the passes around the exchange")
+
+    def _check_bands(self, n_rows: int) -> None:
+        off = band_offsets(int(n_rows), self.world)
+        if min(off[i + 1] - off[i] for i in range(self.world)) <= 0:  # (same verdict on every rank)
+            raise ValueError("the p2p halo transport needs every rank to own rows (use transport='nccl')")
+
+    def reset(self, N, mask, tgt, grad) -> None:
+        self._check_bands(np.asarray(mask).shape[0])
+        super().reset(N, mask, tgt, grad)
+
+    def reset_slab(self, n_rows: int, src_slab, mask_slab, tgt_slab, gradient: str) -> BandPlan:
+        self._check_bands(n_rows)
+        return super().reset_slab(n_rows, src_slab, mask_slab, tgt_slab, gradient)
+
+    def _plan_overlap(self) -> None:
+        """(Re)connect the halo link after a reset.  Collective: every rank calls it."""
+        p = self.plan
+        solver = self.core.solver
+        lo, hi = p.local_band
+        changed = solver.halo_config(lo, hi)
+        flag = self._control_tensor([1.0 if changed else 0.0])
+        self.dist.all_reduce(flag, group=self.group)
+        if float(flag.sum()) == 0.0:
+            return  # same geometry as before on every rank: the link and its counters stay
+        if not changed:
+            solver.halo_config(lo, hi, force=True)
+        mine = (solver.halo_export(solver.UP) if p.up is not None else None,
+                solver.halo_export(solver.DOWN) if p.down is not None else None)
+        blobs = self._all_gather_blobs(mine)
+        if p.up is not None:  # my upper edge rows land in the upper neighbour's box for rows from below
+            solver.halo_connect(solver.UP, blobs[p.up][1], self.same_process)
+        if p.down is not None:
+            solver.halo_connect(solver.DOWN, blobs[p.down][0], self.same_process)
+        self.dist.barrier(self.group)
+
+    def _control_tensor(self, values):
+        import torch
+
+        return torch.tensor(values, dtype=torch.float64, device=self._reduce_device())
+
+    def _all_gather_blobs(self, mine):
+        if hasattr(self.dist, "all_gather_object"):
+            out = [None] * self.world
+            self.dist.all_gather_object(out, mine, group=self.group)
+            return out
+        return self.dist.all_gather_py(mine)  # in-process stand-ins (tests)
+
+    def _reduce_device(self):
+        backend = getattr(self.dist, "get_backend", lambda *_: "nccl")(self.group)
+        return "cpu" if backend == "gloo" else getattr(self.core, "torch_device", "cpu")
+
+    def sweeps(self, iteration: int) -> None:
+        solver = self.core.solver
+        if self.same_process:
+            # Several bands inside ONE process (tests): a stream that waits for a neighbour's rows stalls every
+            # device-wide synchronisation of the process (cudaMalloc / cudaFree, legacy-stream work of torch),
+            # and the neighbour's thread may be the one making that call -- a deadlock that cannot occur between
+            # processes, whose contexts synchronise independently.  So the threads enqueue in lock-step and
+            # leave no wait pending when they go back to host work.
+            self.dist.barrier(self.group)
+            solver.band_sweeps_async(int(iteration))
+            solver.wait()
+            self.dist.barrier(self.group)
+        else:
+            solver.band_sweeps_async(int(iteration))
+        self.exchanges_done = solver.halo_exchanges()
+
+    def exchange(self, which=None) -> None:  # (the base class's NCCL exchange is never used here)
+        raise RuntimeError("P2PBandGridSolver exchanges inside band_sweeps_async")
+
+    def close(self) -> None:
+        pass
+
+
+def make_band_solver(core_solver, dist, group=None, halo: int = 24, overlap: bool = True, transport: str = "p2p",
+                     same_process: bool = False):
+    """Row-band solver over ``fpie_b200.GridSolver`` ``core_solver`` with the halo transport named:
+    ``"p2p"`` (default; the exchange behind the C ABI) or ``"nccl"`` (round 1: ``batch_isend_irecv`` on views
+    of the solver's buffers)."""
+    core = CudaBandCore(core_solver)
+    if transport == "p2p":
+        return P2PBandGridSolver(core, dist, group, halo, overlap, same_process)
+    if transport != "nccl":
+        raise ValueError("transport must be 'p2p' or 'nccl'")
+    solver = BandGridSolver(core, dist, group, halo, overlap)
+    solver.describe = lambda: ("NCCL send/recv, " + ("overlapped with the interior tiles of a pass (second stream)"
+                                                     if solver.exchange_overlaps else "between passes"))
+    solver.close = lambda: None
+    return solver
+
+
 def canonical_crop(mask: np.ndarray):
     """Host-side mask canonicalisation of the Processor (fpie/process.py:338-351), cheap uint8 work:
     threshold on the channel mean, clear the 1-pixel frame, bounding box +-1.
@@ -297,9 +414,17 @@ class BandGridProcessor:
     problem, mpi/grid.cc:34-54) every rank takes the uint8 images and keeps only its slab; ``step``
     returns the full blended target on rank 0 and ``None`` elsewhere (process.py:388-395)."""
 
-    def __init__(self, gradient: str = "max", core=None, dist=None, group=None, halo: int = 24):
+    def __init__(self, gradient: str = "max", core=None, dist=None, group=None, halo: int = 24,
+                 transport: str = "nccl", same_process: bool = False):
+        """``transport="p2p"``: the halo exchange behind the C ABI (``P2PBandGridSolver``; ``core`` must be a
+        ``CudaBandCore``); ``"nccl"``: ``dist.batch_isend_irecv`` on views of the core's buffers (any core)."""
         self.gradient = gradient
-        self.solver = BandGridSolver(core, dist, group, halo)
+        if transport == "p2p":
+            self.solver = P2PBandGridSolver(core, dist, group, halo, same_process=same_process)
+        elif transport == "nccl":
+            self.solver = BandGridSolver(core, dist, group, halo)
+        else:
+            raise ValueError("transport must be 'p2p' or 'nccl'")
         self.dist, self.group = dist, group
         self.rank = self.solver.rank
         self.root = self.rank == 0
@@ -369,8 +494,9 @@ class BandEquProcessor(BandGridProcessor):
     GridSolver and returns the EquSolver's numbers: same fp32 state, same uint8 image, ``reset``
     returns ``K + 1`` and ``step`` scatters only the K solved pixels (process.py:273-280)."""
 
-    def __init__(self, gradient: str = "max", core=None, dist=None, group=None, halo: int = 24):
-        super().__init__(gradient, core, dist, group, halo)
+    def __init__(self, gradient: str = "max", core=None, dist=None, group=None, halo: int = 24,
+                 transport: str = "nccl", same_process: bool = False):
+        super().__init__(gradient, core, dist, group, halo, transport, same_process)
         self.solver.core.set_formulation(True)
 
     def reset(self, src, mask, tgt, mask_on_src=(0, 0), mask_on_tgt=(0, 0)) -> int:

@@ -43,7 +43,7 @@ class BaseProcessor:
         self.root = True
         self.tgt = None
         self.box = None
-        self._canvas = None
+        self._canvas_pool = []
 
     def _require_reset(self) -> None:
         if self.tgt is None or self.box is None:  # the same error the core raises (GridSolver::require_ready)
@@ -63,19 +63,25 @@ class BaseProcessor:
         """Run the device-side reset while a worker thread makes the Processor's private copy of
         the target (process.py:268 / 384); both release the GIL, so they overlap."""
         # page-locked, so that every step's device-to-host copy of the result runs at PCIe speed.  The
-        # reference hands out a fresh copy per reset (`tgt.copy()`); page-locking is too slow for that, so
-        # the previous canvas is recycled -- but only when nobody outside this object can still see it
-        # (the GUI's reset + step per click, fpie/gui.py:96-99, drops the old image first)
+        # reference hands out a fresh copy per reset (`tgt.copy()`); page-locking is too slow for that (tens of
+        # milliseconds for a 50 MB image), so canvases are recycled from a small pool -- but only ones that
+        # nobody outside this object can still see (a caller that keeps the previous result keeps it intact)
+        self.tgt = None
         canvas = None
-        if self._canvas is not None and self._canvas.shape == tgt.shape:
-            self.tgt = None
-            base = self._canvas.base
-            # references: self._canvas + getrefcount's argument; base: the canvas + `base` + the argument
-            if sys.getrefcount(self._canvas) <= 2 and (base is None or sys.getrefcount(base) <= 3):
-                canvas = self._canvas
+        old = None
+        for old in self._canvas_pool:
+            base = old.base
+            # references: the pool's + `old` + getrefcount's argument; base: the canvas + `base` + the argument
+            private = sys.getrefcount(old) <= 3 and (base is None or sys.getrefcount(base) <= 3)
             del base
+            if private and old.shape == tgt.shape:
+                canvas = old
+                break
+        del old
         if canvas is None:
-            canvas = self._canvas = _lib.pinned_empty(tgt.shape, np.uint8)
+            canvas = _lib.pinned_empty(tgt.shape, np.uint8)
+            self._canvas_pool.append(canvas)
+            del self._canvas_pool[:-3]  # (a dropped canvas lives on for as long as its holder keeps it)
         rows = tgt.shape[0]
         parts = 4 if tgt.size >= (8 << 20) else 1  # large images: fault the fresh pages in from several threads
         bounds = [rows * i // parts for i in range(parts + 1)]

@@ -313,6 +313,57 @@ class GridSolver(_Handle):
                                                       ctypes.byref(pitch), ctypes.byref(padr), ctypes.byref(padc)))
         return dict(base=base.value, plane=plane.value, pitch=pitch.value, pad_rows=padr.value, pad_cols=padc.value)
 
+    # -- halo link (row bands; the exchange runs behind the C ABI, csrc/halo.cu) ---------------
+    HALO_BLOB_BYTES = 128
+    UP, DOWN = 0, 1
+
+    def halo_config(self, band_lo: int, band_hi: int, force: bool = False) -> bool:
+        """This slab's own rows are ``[band_lo, band_hi)``; returns True when the link was rebuilt
+        (then ``halo_export`` / ``halo_connect`` are due on both ends)."""
+        changed = ctypes.c_int()
+        _lib.check(self._lib.fpie_b200_grid_halo_config(self.handle, int(band_lo), int(band_hi), int(bool(force)),
+                                                        ctypes.byref(changed)))
+        return bool(changed.value)
+
+    def halo_export(self, side: int) -> bytes:
+        blob = np.zeros(self.HALO_BLOB_BYTES, np.uint8)
+        _lib.check(self._lib.fpie_b200_grid_halo_export(self.handle, int(side), _ptr(blob, ctypes.c_uint8)))
+        return blob.tobytes()
+
+    def halo_connect(self, side: int, blob: bytes, same_process: bool) -> None:
+        buf = np.frombuffer(bytes(blob), np.uint8).copy()
+        if buf.size != self.HALO_BLOB_BYTES:
+            raise ValueError("not a halo blob")
+        _lib.check(self._lib.fpie_b200_grid_halo_connect(self.handle, int(side), _ptr(buf, ctypes.c_uint8),
+                                                         int(bool(same_process))))
+
+    def band_sweeps_async(self, iteration: int) -> None:
+        _lib.check(self._lib.fpie_b200_grid_band_sweeps_async(self.handle, int(iteration)))
+
+    def halo_exchanges(self) -> int:
+        n = ctypes.c_int64()
+        _lib.check(self._lib.fpie_b200_grid_halo_stats(self.handle, ctypes.byref(n)))
+        return n.value
+
+    def halo_debug(self) -> dict:
+        """Counters of the halo link (safe to call from another thread while a step is blocked)."""
+        v = (ctypes.c_int64 * 16)()
+        _lib.check(self._lib.fpie_b200_grid_halo_debug(self.handle, v))
+        v = list(v)
+        return dict(rows=v[0:2], sent=v[2:4], received=v[4:6], flags_up=v[6:8], flags_down=v[8:10], current=v[10],
+                    block_k=v[11], variant=v[12], edge_tiles=v[13], interior_tiles=v[14], pending=v[15])
+
+    def halo_trace_begin(self, max_intervals: int) -> None:
+        _lib.check(self._lib.fpie_b200_grid_halo_trace_begin(self.handle, int(max_intervals)))
+
+    def halo_trace(self):
+        """``[(tag, ms), ...]`` of the traced intervals (see include/fpie_b200.h); synchronises."""
+        out = np.zeros(8192, np.float32)
+        n = ctypes.c_int()
+        _lib.check(self._lib.fpie_b200_grid_halo_trace_read(self.handle, _ptr(out, ctypes.c_float), out.size,
+                                                            ctypes.byref(n)))
+        return [(int(out[i]), float(out[i + 1])) for i in range(0, n.value, 2)]
+
     def current_buffer(self) -> int:
         which = ctypes.c_int()
         _lib.check(self._lib.fpie_b200_grid_band_current(self.handle, ctypes.byref(which)))

@@ -186,6 +186,41 @@ int fpie_b200_grid_set_edge_rows(fpie_b200_grid *g, int rows);
 int fpie_b200_grid_pass_async(fpie_b200_grid *g, int nsweeps, int part);
 int fpie_b200_grid_flip(fpie_b200_grid *g);
 
+/* The halo exchange as a data plane behind this ABI (csrc/halo.cu): copy-engine peer copies over NVLink and
+ * stream memory operations instead of a communication library's SM kernels.  Call sequence per slab, after
+ * every reset:
+ *   halo_config(band_lo, band_hi)     the slab's rows [band_lo, band_hi) are its own band, the rows above /
+ *                                     below are halo rows (0 rows on a side = no neighbour there); also sets the
+ *                                     residual row window and the edge / interior split of the tile list.
+ *                                     Returns *changed = 1 when the link had to be rebuilt (first call, new
+ *                                     geometry, or force_rebuild): only then are export / connect needed again --
+ *                                     on BOTH ends of a link, so a caller whose neighbour reports a rebuild calls
+ *                                     again with force_rebuild = 1.
+ *   halo_export(side, blob[128])      an opaque description of this slab's receive box for that side
+ *                                     (side 0 = up, 1 = down), to be handed to the neighbour on that side
+ *   halo_connect(side, blob, same_process)   the NEIGHBOUR's blob for the box that takes this slab's rows;
+ *                                     between processes the box is mapped with cudaIpcOpenMemHandle
+ *   band_sweeps_async(iters)          `iters` sweeps with a halo exchange every `halo` sweeps, overlapped with
+ *                                     the interior tiles of the passes around it; every band of the problem must
+ *                                     make the same call (the neighbours wait for each other's rows)
+ * Replaces the blocking one-row MPI_Sendrecv of fpie/core/mpi/grid.cc:118-135. */
+#define FPIE_B200_HALO_BLOB_BYTES 128
+int fpie_b200_grid_halo_config(fpie_b200_grid *g, int band_lo, int band_hi, int force_rebuild, int *changed);
+int fpie_b200_grid_halo_export(fpie_b200_grid *g, int side, unsigned char *blob);
+int fpie_b200_grid_halo_connect(fpie_b200_grid *g, int side, const unsigned char *blob, int same_process);
+int fpie_b200_grid_band_sweeps_async(fpie_b200_grid *g, int iters);
+/* Exchanges started so far; and a phase trace of the first `max_intervals` exchange intervals of the next
+ * band_sweeps_async call: pairs (tag, milliseconds since the first mark) -- tags 1-6 = solver stream before /
+ * after the edge and interior parts of a pass, 10/11 = halo stream around the peer copies, 20/21 = solver
+ * stream around the wait for the neighbours' rows.  trace_read synchronises; returns the floats written. */
+int fpie_b200_grid_halo_stats(fpie_b200_grid *g, int64_t *exchanges);
+/* Link counters for diagnostics, readable while the solver's streams are blocked on a neighbour: out16 =
+ * {rows[2], sent[2], received[2], flag words [side][parity] (4), current buffer, block_k, variant, edge tile
+ * entries, interior tile entries, exchange pending} (-1 = not available). */
+int fpie_b200_grid_halo_debug(fpie_b200_grid *g, int64_t *out16);
+int fpie_b200_grid_halo_trace_begin(fpie_b200_grid *g, int max_intervals);
+int fpie_b200_grid_halo_trace_read(fpie_b200_grid *g, float *out, int max_floats, int *written);
+
 /* Formulation built by the image-level resets (reset_from_images / reset_slab) that follow:
  * 0 (default) = GridSolver's (unmasked pixels hold the target, fpie/process.py:354-378);
  * 1 = EquSolver's, laid out on the grid: unknowns carry X = target and B = grad + the targets of

@@ -191,6 +191,18 @@ class ThreadDist:
     def barrier(self, group=None):
         self.bar.wait()
 
+    def get_backend(self, group=None):
+        return "threads"
+
+    def all_gather_py(self, obj):
+        """Every rank's python object, in rank order (what ``all_gather_object`` returns)."""
+        me = self.local.rank
+        self.slots[me] = obj
+        self.bar.wait()
+        out = list(self.slots)
+        self.bar.wait()
+        return out
+
     def batch_isend_irecv(self, ops):
         me = self.local.rank
         for op in ops:

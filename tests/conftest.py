@@ -4,6 +4,14 @@ import sys
 import numpy as np
 import pytest
 
+# Several bands of one problem live in ONE process in the GPU tests, and the halo link waits on flag words at
+# stream level: streams that alias one hardware queue would turn such a wait into a false dependency on the
+# neighbour's sends.  Give every stream its own queue (must be set before CUDA initialises).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# ... and a kernel's first launch must not fall into such a wait: CUDA loads kernels lazily and a load may
+# synchronise the context (the library also pre-loads what a band step launches, GridSolver::preload_kernels)
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG_ROOT = os.path.join(ROOT, "fast-poisson-image-editing_b200")
 for p in (ROOT, PKG_ROOT):

@@ -23,10 +23,26 @@ from oracle import c_oracle, np_oracle
 pytestmark = pytest.mark.gpu
 
 
-def _run_threads(world, halo, make_and_reset, steps):
+TRANSPORTS = ["p2p", "nccl"]  # "nccl" on ThreadDist = the round-1 schedule with device copies standing in for NCCL
+
+
+def _thread_core(transport):
+    """One band's GridSolver inside a thread.  The p2p link waits on flag words AT STREAM LEVEL, so two bands
+    of one process must not share a stream (the wait of one would block the other's sends): each gets its own."""
     import torch
 
     import fpie_b200
+
+    if transport != "p2p":
+        return fpie_b200.GridSolver(8, 8, device=0), None
+    stream = torch.cuda.Stream(device=0)
+    with torch.cuda.stream(stream):
+        return fpie_b200.GridSolver(8, 8, device=0), stream
+
+
+def _run_threads(world, halo, make_and_reset, steps, transport="p2p"):
+    import torch
+
     from fpie_b200 import band
 
     dist = ThreadDist(world)
@@ -37,12 +53,13 @@ def _run_threads(world, halo, make_and_reset, steps):
         try:
             dist.bind(rank)
             torch.cuda.set_device(0)
-            solver = band.BandGridSolver(band.CudaBandCore(fpie_b200.GridSolver(8, 8, device=0)), dist, halo=halo)
+            core, stream = _thread_core(transport)
+            solver = band.make_band_solver(core, dist, halo=halo, transport=transport, same_process=True)
             make_and_reset(solver)
             solver.sync()
             for it in steps:
                 img, err = solver.step(it)
-            out[rank] = (solver.plan, solver.band_state(), img, err)
+            out[rank] = (solver.plan, solver.band_state(), img, err, getattr(solver, "exchanges_done", None))
         except Exception as exc:  # surface in the main thread
             errors.append(exc)
             try:
@@ -60,22 +77,26 @@ def _run_threads(world, halo, make_and_reset, steps):
     return out
 
 
-@pytest.mark.parametrize("world,halo,steps", [(2, 8, (37,)), (3, 16, (5, 40)), (4, 24, (64,))])
-def test_thread_bands_core_level(world, halo, steps):
+@pytest.mark.parametrize("transport", TRANSPORTS)
+@pytest.mark.parametrize("world,halo,steps", [(2, 8, (37,)), (3, 16, (5, 40)), (4, 24, (64,)), (2, 24, (100, 3, 48))])
+def test_thread_bands_core_level(world, halo, steps, transport):
     shape = (530, 301)
     mask, tgt, grad = random_grid(*shape, seed=8)
-    out = _run_threads(world, halo, lambda s: s.reset(mask.size, mask, tgt, grad), steps)
+    out = _run_threads(world, halo, lambda s: s.reset(mask.size, mask, tgt, grad), steps, transport)
     want = c_oracle.grid_sweeps(mask, tgt, grad, sum(steps))
     got = np.zeros_like(want)
-    for plan, state, img, err in out:
+    if transport == "p2p":  # one exchange per started interval of `halo` sweeps, in every step
+        assert all(o[4] == sum(-(-it // halo) for it in steps) for o in out)
+    for plan, state, img, err, _ in out:
         got[plan.band_lo : plan.band_hi] = state
         np.testing.assert_array_equal(img, c_oracle.clip_u8(want[plan.band_lo : plan.band_hi]))
         np.testing.assert_allclose(err, c_oracle.grid_residual(mask, want, grad)[1], rtol=1e-5)
     np.testing.assert_array_equal(got, want)
 
 
+@pytest.mark.parametrize("transport", TRANSPORTS)
 @pytest.mark.parametrize("kind", ["square", "circle"])
-def test_thread_bands_from_image_slabs(kind):
+def test_thread_bands_from_image_slabs(kind, transport):
     """Each band uploads only its slab of the uint8 images (reset_slab)."""
     from fpie_b200 import band, synth
 
@@ -91,18 +112,18 @@ def test_thread_bands_from_image_slabs(kind):
         sl = slice(p.slab_lo, p.slab_hi)
         solver.reset_slab(x1 - x0, csrc[sl], cmask[sl], ctgt[sl], "max")
 
-    out = _run_threads(world, halo, reset, (iters,))
+    out = _run_threads(world, halo, reset, (iters,), transport)
     want = c_oracle.grid_sweeps(mc, tcrop, g, iters)
-    for plan, state, img, err in out:
+    for plan, state, img, err, _ in out:
         np.testing.assert_array_equal(state, want[plan.band_lo : plan.band_hi])
         np.testing.assert_allclose(err, c_oracle.grid_residual(mc, want, g)[1], rtol=1e-5)
 
 
-def test_thread_band_processor_image_level():
+@pytest.mark.parametrize("transport", TRANSPORTS)
+def test_thread_band_processor_image_level(transport):
     """BandGridProcessor: full images in on every rank, blended target out on rank 0."""
     import torch
 
-    import fpie_b200
     from fpie_b200 import band, synth
 
     src, mask, tgt = synth.make_problem("star", 600, 500, seed=12)
@@ -115,7 +136,9 @@ def test_thread_band_processor_image_level():
         try:
             dist.bind(rank)
             torch.cuda.set_device(0)
-            proc = band.BandGridProcessor("max", band.CudaBandCore(fpie_b200.GridSolver(8, 8, device=0)), dist, halo=16)
+            core, stream = _thread_core(transport)
+            proc = band.BandGridProcessor("max", band.CudaBandCore(core), dist, halo=16, transport=transport,
+                                          same_process=True)
             n = proc.reset(src, mask, big_tgt, (0, 0), (40, 70))
             proc.sync()
             proc.step(20)
@@ -144,8 +167,9 @@ def test_thread_band_processor_image_level():
     np.testing.assert_allclose(err, werr, rtol=1e-4)
 
 
+@pytest.mark.parametrize("transport", TRANSPORTS)
 @pytest.mark.parametrize("kind,world,halo", [("star", 3, 16), ("holes", 2, 24), ("ring", 4, 8)])
-def test_thread_band_equ_processor_matches_single_gpu_equ_solver(kind, world, halo):
+def test_thread_band_equ_processor_matches_single_gpu_equ_solver(kind, world, halo, transport):
     """BandEquProcessor (EquSolver arithmetic on row bands) == EquProcessor on one GPU: same unknowns
     bit for bit, same blended image, same N; err within tolerance."""
     import torch
@@ -168,7 +192,9 @@ def test_thread_band_equ_processor_matches_single_gpu_equ_solver(kind, world, ha
         try:
             dist.bind(rank)
             torch.cuda.set_device(0)
-            proc = band.BandEquProcessor("max", band.CudaBandCore(fpie_b200.GridSolver(8, 8, device=0)), dist, halo=halo)
+            core, stream = _thread_core(transport)
+            proc = band.BandEquProcessor("max", band.CudaBandCore(core), dist, halo=halo, transport=transport,
+                                         same_process=True)
             got_n = proc.reset(src, mask, big_tgt, (0, 0), (31, 52))
             proc.sync()
             proc.step(30)
@@ -214,7 +240,10 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _nccl_worker(rank, world, port, out_dir):
+def _band_worker(rank, world, port, out_dir, backend, transport, devices, shape, halo, steps):
+    """One band in its own process.  ``backend`` is the control plane (nccl: one process per GPU; gloo: the
+    processes may share a GPU -- the halo rows then cross process boundaries through CUDA IPC on one device,
+    the same code path as between GPUs)."""
     for p in (ROOT, PKG_ROOT, os.path.join(ROOT, "tests")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -225,32 +254,60 @@ def _nccl_worker(rank, world, port, out_dir):
     from fpie_b200 import band
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world)
+    dev = devices[rank]
+    torch.cuda.set_device(dev)
+    dist.init_process_group(backend, rank=rank, world_size=world)
     try:
-        mask, tgt, grad = random_grid(900, 517, seed=2)
-        solver = band.BandGridSolver(band.CudaBandCore(fpie_b200.GridSolver(8, 8, device=rank)), dist, halo=16)
-        solver.reset(mask.size, mask, tgt, grad)
-        solver.sync()
-        solver.step(20)
-        img, err = solver.step(45)
+        mask, tgt, grad = random_grid(*shape, seed=2)
+        solver = band.make_band_solver(fpie_b200.GridSolver(8, 8, device=dev), dist, halo=halo, transport=transport)
+        for round_ in range(2):  # the second reset keeps the link (same geometry) and its counters
+            solver.reset(mask.size, mask, tgt, grad)
+            solver.sync()
+            for it in steps:
+                img, err = solver.step(it)
         p = solver.plan
-        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), state=solver.band_state(), err=err, lo=p.band_lo, hi=p.band_hi)
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), state=solver.band_state(), err=err, lo=p.band_lo, hi=p.band_hi,
+                 img=img, exchanges=getattr(solver, "exchanges_done", -1))
     finally:
         dist.destroy_process_group()
 
 
-def test_nccl_bands(tmp_path):
+def _check_band_files(tmp_path, world, shape, steps):
+    mask, tgt, grad = random_grid(*shape, seed=2)
+    want = c_oracle.grid_sweeps(mask, tgt, grad, sum(steps))
+    for r in range(world):
+        z = np.load(tmp_path / f"rank{r}.npz")
+        np.testing.assert_array_equal(z["state"], want[int(z["lo"]) : int(z["hi"])])
+        np.testing.assert_array_equal(z["img"], c_oracle.clip_u8(want[int(z["lo"]) : int(z["hi"])]))
+        np.testing.assert_allclose(z["err"], c_oracle.grid_residual(mask, want, grad)[1], rtol=1e-5)
+    return [int(np.load(tmp_path / f"rank{r}.npz")["exchanges"]) for r in range(world)]
+
+
+@pytest.mark.parametrize("world,halo,steps", [(2, 16, (20, 45)), (3, 24, (130,))])
+def test_ipc_bands_processes_sharing_one_gpu(tmp_path, world, halo, steps):
+    """The SHIPPED multi-GPU transport on a one-GPU box: one process per band, all on cuda:0, gloo as the
+    control plane, halo rows through cudaIpcOpenMemHandle-mapped receive boxes, flag words and stream-level
+    waits -- exactly what runs between GPUs, minus NVLink."""
+    import torch.multiprocessing as mp
+
+    shape = (900, 517)
+    mp.spawn(_band_worker, args=(world, _free_port(), str(tmp_path), "gloo", "p2p", [0] * world, shape, halo, steps),
+             nprocs=world, join=True)
+    exchanges = _check_band_files(tmp_path, world, shape, steps)
+    assert all(e == 2 * sum(-(-it // halo) for it in steps) for e in exchanges)
+
+
+@pytest.mark.parametrize("transport", TRANSPORTS)
+def test_multi_gpu_bands(tmp_path, transport):
+    """One process per GPU over NCCL (skipped on a one-GPU box; bench.py --gpus N checks the same path in
+    every multi-GPU run and reports it as `parity`)."""
     import torch
     import torch.multiprocessing as mp
 
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
-    mp.spawn(_nccl_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
-    mask, tgt, grad = random_grid(900, 517, seed=2)
-    want = c_oracle.grid_sweeps(mask, tgt, grad, 65)
-    for r in range(world):
-        z = np.load(tmp_path / f"rank{r}.npz")
-        np.testing.assert_array_equal(z["state"], want[int(z["lo"]) : int(z["hi"])])
-        np.testing.assert_allclose(z["err"], c_oracle.grid_residual(mask, want, grad)[1], rtol=1e-5)
+    shape, steps = (900, 517), (20, 45)
+    mp.spawn(_band_worker, args=(world, _free_port(), str(tmp_path), "nccl", transport, list(range(world)), shape, 16,
+                                 steps), nprocs=world, join=True)
+    _check_band_files(tmp_path, world, shape, steps)
