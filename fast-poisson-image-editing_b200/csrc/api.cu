@@ -123,6 +123,19 @@ API int fpie_b200_grid_flip(fpie_b200_grid *g) {
   NEED(g);
   return guarded([&] { g->impl.flip(); });
 }
+API int fpie_b200_grid_patch_info(fpie_b200_grid *g, int *usable, int *rows_per_thread, int *cols_per_thread, int *cluster,
+                                  int64_t *launches) {
+  NEED(g);
+  return guarded([&] {
+    int r = 0, c = 0, cl = 0;
+    const bool ok = g->impl.patch_usable(&r, &c, &cl);
+    if (usable) *usable = ok ? 1 : 0;
+    if (rows_per_thread) *rows_per_thread = r;
+    if (cols_per_thread) *cols_per_thread = c;
+    if (cluster) *cluster = cl;
+    if (launches) *launches = g->impl.patch_launches() | ((int64_t)g->impl.patch_clusters() << 40);
+  });
+}
 API int fpie_b200_grid_halo_config(fpie_b200_grid *g, int band_lo, int band_hi, int force_rebuild, int *changed) {
   NEED(g);
   return guarded([&] {

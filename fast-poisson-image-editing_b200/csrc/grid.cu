@@ -458,6 +458,7 @@ grid_sweepk_pipe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
 
 }  // namespace fpie
 #include "grid_pair.cuh"
+#include "patch.cuh"
 namespace fpie {
 
 // Classify the tile grid: flag bit0 = some masked pixel in the stored (inner)
@@ -711,6 +712,13 @@ GridSolver::GridSolver(int device, cudaStream_t stream, int block_k, int variant
   serpentine_ = !(no_serp && no_serp[0] && no_serp[0] != '0');
   const char *no_graph = getenv("FPIE_B200_NO_GRAPH");
   graph_off_ = no_graph && no_graph[0] && no_graph[0] != '0';
+  // the persistent small-image kernel: FPIE_B200_PATCH=0 switches it off (A/B against the mosaic path),
+  // FPIE_B200_PATCH_ROWS=4|8 overrides the rows per thread
+  const char *patch = getenv("FPIE_B200_PATCH");
+  patch_off_ = patch && patch[0] == '0';
+  const char *prow = getenv("FPIE_B200_PATCH_ROWS");
+  patch_rows_ = prow ? atoi(prow) : 0;
+  if (patch_rows_ != 4 && patch_rows_ != 8) patch_rows_ = 0;
 }
 
 GridSolver::~GridSolver() {
@@ -819,6 +827,7 @@ void GridSolver::reset(int n, int m, const int32_t *mask, int64_t mask_rs, int64
   FPIE_REQUIRE(mask_cs == 1 && mask_rs >= m, "GridSolver.reset: mask rows must be contiguous (column stride 1)");
   DeviceGuard guard(device_);
   ready_ = false;
+  zeroed_ = PlaneGeom{};
   batch_ = BatchMap{0, 0, 0, 0};
   layout(n, m);
   const PlaneGeom &g = geom_;
@@ -892,6 +901,7 @@ void GridSolver::reset_batch(const uint8_t *src, const uint8_t *mask, const uint
 void GridSolver::reset_from_equ(const EquEmbed &e) {
   DeviceGuard guard(device_);
   ready_ = false;
+  zeroed_ = PlaneGeom{};
   batch_ = BatchMap{0, 0, 0, 0};
   layout(e.n, e.m);
   const PlaneGeom &g = geom_;
@@ -930,10 +940,24 @@ void GridSolver::build_from_upload() {
   hq_.resize((size_t)g.plane * 3);
   bits_.resize((size_t)g.rows * g.wpitch);
   img_.resize((size_t)g.n * g.m * 3);
-  CUDA_CHECK(cudaMemsetAsync(x_[0].ptr, 0, x_[0].bytes(), stream_));
-  CUDA_CHECK(cudaMemsetAsync(x_[1].ptr, 0, x_[1].bytes(), stream_));
-  CUDA_CHECK(cudaMemsetAsync(hq_.ptr, 0, hq_.bytes(), stream_));
-  CUDA_CHECK(cudaMemsetAsync(bits_.ptr, 0, bits_.bytes(), stream_));
+  // The build kernel writes every pixel and mask word of the n x m grid; only the padding around it has to be
+  // zeroed, and it stays zero (no kernel ever writes padding).  A reset on the geometry of the previous one
+  // (the GUI, repeated blends of one size) therefore skips 0.6 GB of memsets at 4096^2.
+  const bool clean = zeroed_.n == g.n && zeroed_.m == g.m && zeroed_.rows == g.rows && zeroed_.pitch == g.pitch &&
+                     zeroed_ptr_[0] == x_[0].ptr && zeroed_ptr_[1] == x_[1].ptr && zeroed_ptr_[2] == hq_.ptr &&
+                     zeroed_ptr_[3] == (float *)bits_.ptr && batch_.batch == 0 && !zeroed_batch_;
+  if (!clean) {
+    CUDA_CHECK(cudaMemsetAsync(x_[0].ptr, 0, x_[0].bytes(), stream_));
+    CUDA_CHECK(cudaMemsetAsync(x_[1].ptr, 0, x_[1].bytes(), stream_));
+    CUDA_CHECK(cudaMemsetAsync(hq_.ptr, 0, hq_.bytes(), stream_));
+    CUDA_CHECK(cudaMemsetAsync(bits_.ptr, 0, bits_.bytes(), stream_));
+  }
+  zeroed_ = g;
+  zeroed_ptr_[0] = x_[0].ptr;
+  zeroed_ptr_[1] = x_[1].ptr;
+  zeroed_ptr_[2] = hq_.ptr;
+  zeroed_ptr_[3] = (float *)bits_.ptr;
+  zeroed_batch_ = batch_.batch > 0;
   CUDA_CHECK(cudaMemsetAsync(err_.ptr, 0, err_.bytes(), stream_));
   const long long warps = (long long)g.n * g.wpitch;
   grid_build_kernel<<<blocks_for(warps * 32, 256), 256, 0, stream_>>>(
@@ -1299,12 +1323,118 @@ void GridSolver::make_tensor_maps() {
   tm_m_ = make_mask_tensor_map(bits_.ptr, g.wpitch, g.rows, MASK_BOX_WORDS, shape_.tile_h());
 }
 
+namespace {
+
+struct PatchArgs {
+  PlaneGeom g;
+  BatchMap bm;
+  float *x;
+  const float *hq;
+  const uint32_t *bits;
+  int nsweeps, nitems, cluster, sm_count;
+  cudaStream_t stream;
+};
+
+// one persistent launch: every cluster of `cluster` CTAs walks over (patch, plane) items
+template <int R, int NW, int CPT, bool FRAME>
+int launch_patch_t(const PatchArgs &a) {
+  auto kernel = grid_patch_kernel<R, NW, CPT, FRAME>;
+  constexpr size_t smem = sizeof(PatchSmem<NW, CPT>);
+  CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(NW * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = a.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = a.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // how many clusters the device can hold at once (a cluster lives inside one GPC)
+  cfg.gridDim = dim3(a.cluster);
+  int max_clusters = 0;
+  cfg.gridDim = dim3(a.cluster * a.sm_count);  // (the query wants a grid to reason about)
+  CUDA_CHECK(cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg));
+  FPIE_REQUIRE(max_clusters > 0, "the persistent patch kernel does not fit this device");
+  const int clusters = std::min(a.nitems, max_clusters);
+  cfg.gridDim = dim3(clusters * a.cluster);
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, a.g, a.bm, a.x, a.hq, a.bits, a.nsweeps, a.nitems));
+  return clusters;
+}
+
+template <int R, int CPT>
+int launch_patch_f(const PatchArgs &a, bool frame) {
+  return frame ? launch_patch_t<R, 8, CPT, true>(a) : launch_patch_t<R, 8, CPT, false>(a);
+}
+
+}  // namespace
+
+// Small patches / small images: the persistent cluster kernel of patch.cuh.  A (patch, plane) needs
+// ceil(rows / (8 warps x R rows)) CTAs of one cluster (<= 8, the portable limit) and at most 256 columns.
+bool GridSolver::patch_shape(int *rows_per_thread, int *cols_per_thread, int *cluster) const {
+  // (an explicit tile shape or blocking depth is a request for the tiled kernel)
+  if (patch_off_ || !auto_tune_ || !auto_k_) return false;
+  const bool single = batch_.batch == 0;
+  const int ph = single ? geom_.n : batch_.ph, pw = single ? geom_.m : batch_.pw;
+  if (pw > 256 || ph > 512) return false;
+  const int cpt = pw <= 128 ? 4 : 8;
+  int r = patch_rows_ > 0 ? patch_rows_ : (ph <= 256 ? 4 : 8);
+  if (ceil_div(ph, 8 * r) > 8) r = 8;
+  const int cl = (int)ceil_div(ph, 8 * r);
+  if (cl > 8) return false;
+  if (rows_per_thread) *rows_per_thread = r;
+  if (cols_per_thread) *cols_per_thread = cpt;
+  if (cluster) *cluster = cl;
+  return true;
+}
+
+void GridSolver::patch_sweeps(int iters) {
+  int r = 0, cpt = 0, cl = 0;
+  patch_shape(&r, &cpt, &cl);
+  const bool single = batch_.batch == 0;
+  PatchArgs a{};
+  a.g = geom_;
+  a.bm = single ? BatchMap{1, geom_.n, geom_.m, 1} : batch_;
+  a.x = x_[cur_].ptr;
+  a.hq = hq_.ptr;
+  a.bits = bits_.ptr;
+  a.nsweeps = iters;
+  a.nitems = a.bm.batch * 3;
+  a.cluster = cl;
+  a.sm_count = sm_count_;
+  a.stream = stream_;
+  // every pixel but the 1-pixel frame of every patch is an unknown, and the patch fills the cluster's rows and
+  // the warp's columns exactly: the select-free instruction stream
+  const bool frame = stats_.unknowns == (int64_t)a.bm.batch * (a.bm.ph - 2) * (a.bm.pw - 2) &&
+                     a.bm.ph == cl * 8 * r && a.bm.pw == 32 * cpt;
+  if (r == 4 && cpt == 8)
+    patch_clusters_ = launch_patch_f<4, 8>(a, frame);
+  else if (r == 8 && cpt == 8)
+    patch_clusters_ = launch_patch_f<8, 8>(a, frame);
+  else if (r == 4 && cpt == 4)
+    patch_clusters_ = launch_patch_f<4, 4>(a, frame);
+  else if (r == 8 && cpt == 4)
+    patch_clusters_ = launch_patch_f<8, 4>(a, frame);
+  else
+    throw Error("fpie_b200: no persistent patch kernel for this shape");
+  stats_.launches += 1;
+  patch_launches_ += 1;
+  CUDA_CHECK(cudaGetLastError());
+}
+
 void GridSolver::sweeps_async(int iters) {
   require_ready();
   FPIE_REQUIRE(iters >= 0, "step: negative iteration count");
   DeviceGuard guard(device_);
   const PlaneGeom &g = geom_;
   if (stats_.unknowns == 0 || iters == 0) return;
+  // batches of small patches and single small images: one persistent launch, the state never leaves the SMs
+  if ((batch_.batch > 0 || patch_single_) && iters >= patch_min_iters_ && patch_shape(nullptr, nullptr, nullptr)) {
+    patch_sweeps(iters);
+    return;
+  }
   if (variant_ == 1) {
     const long long work = (long long)g.n * g.groups * 3;
     for (int i = 0; i < iters; ++i) {

@@ -97,6 +97,9 @@ class GridSolver {
   int current() const { return cur_; }
   void config(int *variant, int *rows, int *warps, int *occ) const;
   const GridStats &stats() const { return stats_; }
+  int64_t patch_launches() const { return patch_launches_; }
+  int patch_clusters() const { return patch_clusters_; }
+  bool patch_usable(int *r, int *c, int *cl) const { return ready_ && patch_shape(r, c, cl); }
   const PlaneGeom &geom() const { return geom_; }
 
  private:
@@ -124,6 +127,9 @@ class GridSolver {
 
   bool ready_ = false;
   PlaneGeom geom_{};
+  PlaneGeom zeroed_{};             // geometry whose padding is known to be zero in the buffers below
+  const float *zeroed_ptr_[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool zeroed_batch_ = false;
   int cur_ = 0;
   int win_lo_ = 0, win_hi_ = 0;
   DeviceBuffer<float> x_[2];
@@ -147,6 +153,12 @@ class GridSolver {
   cudaStream_t cap_stream_ = nullptr;
   cudaGraphExec_t graph_[2] = {nullptr, nullptr};
   bool graph_off_ = false, graph_warm_ = false;
+  bool patch_off_ = false;      // persistent small-image kernel disabled
+  bool patch_single_ = true;    // ... also used for single (unbatched) small grids
+  int patch_rows_ = 0;          // rows per thread override (0 = automatic)
+  int patch_min_iters_ = 32;    // shorter runs stay on the tiled kernel (the persistent launch reads and writes the planes once)
+  int64_t patch_launches_ = 0;
+  int patch_clusters_ = 0;      // clusters of the last persistent launch
   bool serpentine_ = true;  // alternate passes walk the tile list in opposite directions
   // edge / interior partition of the tile list (set_edge_rows)
   std::vector<int2> host_tiles_;
@@ -176,6 +188,8 @@ class GridSolver {
   void halo_recv(int which);
   void run_pass(int nsweeps, const int2 *tiles, int ntiles);
   void preload_kernels();
+  bool patch_shape(int *rows_per_thread, int *cols_per_thread, int *cluster) const;
+  void patch_sweeps(int iters);
   HaloSide halo_[2];
   int band_lo_ = 0, band_hi_ = 0;
   bool halo_pending_ = false;

@@ -44,6 +44,7 @@ SIGNATURES = {
     "fpie_b200_grid_sync": [c_void_p],
     "fpie_b200_grid_fetch": [c_void_p, u8p, f32p],
     "fpie_b200_grid_fetch_rows": [c_void_p, c_int, c_int, u8p, f32p],
+    "fpie_b200_grid_patch_info": [c_void_p, intp, intp, intp, intp, i64p],
     "fpie_b200_grid_halo_config": [c_void_p, c_int, c_int, c_int, intp],
     "fpie_b200_grid_halo_export": [c_void_p, c_int, u8p],
     "fpie_b200_grid_halo_connect": [c_void_p, c_int, u8p, c_int],

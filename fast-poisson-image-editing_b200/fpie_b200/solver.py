@@ -302,6 +302,15 @@ class GridSolver(_Handle):
                     total_tiles=tot.value, variant=v.value, tile=(rows.value * warps.value, 128),
                     rows_per_thread=rows.value, warps=warps.value, ctas_per_sm=occ.value)
 
+    def patch_info(self) -> dict:
+        """The persistent small-image kernel for the current problem: usable?, thread tile, cluster size, launches."""
+        u, r, c, cl = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        n = ctypes.c_int64()
+        _lib.check(self._lib.fpie_b200_grid_patch_info(self.handle, ctypes.byref(u), ctypes.byref(r), ctypes.byref(c),
+                                                       ctypes.byref(cl), ctypes.byref(n)))
+        return dict(usable=bool(u.value), rows_per_thread=r.value, cols_per_thread=c.value, cluster=cl.value,
+                    launches=n.value & ((1 << 40) - 1), clusters=n.value >> 40)
+
     def set_row_window(self, lo: int, hi: int) -> None:
         _lib.check(self._lib.fpie_b200_grid_set_row_window(self.handle, int(lo), int(hi)))
 

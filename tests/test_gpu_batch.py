@@ -83,3 +83,97 @@ def test_config5_sized_batch():
         canvas, e64, _ = _oracle_patch(src[i], mask[i], tgt[i], "src", 120)
         np.testing.assert_array_equal(out[i], canvas)
         np.testing.assert_allclose(err[i], e64, rtol=1e-4, atol=1e-3)
+
+
+# ---- the persistent small-image kernel (csrc/patch.cuh) ---------------------------------------------
+# Steps of >= 32 sweeps on patches / images of at most 512 x 256 pixels run as ONE launch in which a
+# cluster keeps each (patch, plane) in registers.  Same arithmetic as the tiled kernel: every result
+# below must be bit-identical to the oracle and to the mosaic path.
+
+
+def _full_batch(b, n, m, seed):
+    rng = np.random.default_rng(seed)
+    src = rng.integers(0, 256, (b, n, m, 3), dtype=np.uint8)
+    tgt = rng.integers(0, 256, (b, n, m, 3), dtype=np.uint8)
+    return src, np.full((b, n, m), 255, np.uint8), tgt
+
+
+@pytest.mark.parametrize("b,n,m,iters,full", [
+    (5, 256, 256, 64, True),    # config 5 shape, full-square masks: the select-free (frame-only) stream, cluster of 8
+    (5, 256, 256, 45, False),   # ... arbitrary masks: per-pixel selects
+    (3, 64, 64, 100, True),     # 4 columns per thread, cluster of 2
+    (4, 100, 128, 33, False),   # rows do not fill the cluster (padding rows), 4 columns per thread
+    (3, 200, 252, 40, False),   # columns do not fill the warp
+    (2, 300, 256, 37, True),    # 8 rows per thread (more than 256 rows)
+    (2, 512, 200, 35, False),   # the tallest supported patch
+    (40, 32, 32, 50, False),    # more clusters than the device holds at once: the persistent loop
+])
+def test_persistent_kernel_matches_oracle_and_mosaic(b, n, m, iters, full, monkeypatch):
+    import fpie_b200
+
+    src, mask, tgt = _full_batch(b, n, m, seed=n + m) if full else _batch(b, n, m, seed=n + m)
+    proc = fpie_b200.BatchGridProcessor("max", "b200")
+    proc.reset(src, mask, tgt)
+    info = proc.core.patch_info()
+    assert info["usable"] and info["cluster"] == -(-n // (8 * info["rows_per_thread"]))
+    assert info["cols_per_thread"] == (4 if m <= 128 else 8)
+    out, err = proc.step(iters)
+    assert proc.core.patch_info()["launches"] == 1 and proc.core.info()["launches"] < 12
+    state = proc.core.batch_state()
+    for i in range(b):
+        canvas, e64, fullstate = _oracle_patch(src[i], mask[i], tgt[i], "max", iters)
+        np.testing.assert_array_equal(state[i], fullstate)
+        np.testing.assert_array_equal(out[i], canvas)
+        np.testing.assert_allclose(err[i], e64, rtol=1e-4, atol=1e-3)
+    # a second step continues from the state the kernel wrote back; the mosaic path (persistent kernel off)
+    # gives the same bits
+    out2, err2 = proc.step(iters + 1)
+    monkeypatch.setenv("FPIE_B200_PATCH", "0")
+    ref = fpie_b200.BatchGridProcessor("max", "b200")
+    ref.reset(src, mask, tgt)
+    assert not ref.core.patch_info()["usable"]
+    ref.step(iters)
+    want2, werr2 = ref.step(iters + 1)
+    np.testing.assert_array_equal(out2, want2)
+    np.testing.assert_array_equal(proc.core.batch_state(), ref.core.batch_state())
+    np.testing.assert_allclose(err2, werr2, rtol=1e-6)
+
+
+@pytest.mark.parametrize("kind,n,m", [("circle", 256, 256), ("star", 180, 140), ("holes", 96, 250), ("square", 400, 256)])
+@pytest.mark.parametrize("rows", ["4", "8"])
+def test_persistent_kernel_single_images(kind, n, m, rows, monkeypatch):
+    """One small image through the ordinary GridProcessor / EquProcessor: the GUI's reset + step per click."""
+    import fpie_b200
+    from fpie_b200 import synth
+
+    monkeypatch.setenv("FPIE_B200_PATCH_ROWS", rows)
+    src, mask, tgt = synth.make_problem(kind, n, m, seed=7)
+    proc = fpie_b200.GridProcessor("avg", "b200")
+    proc.reset(src, mask, tgt, (0, 0), (0, 0))
+    out, err = proc.step(90)
+    assert proc.core.patch_info()["launches"] == 1
+    proc.step(10)  # (a short step stays on the tiled kernel)
+    assert proc.core.patch_info()["launches"] == 1
+    out, err = proc.step(50)
+    want = np_oracle.GridOracle("avg")
+    want.reset(src, mask, tgt)
+    want.t = c_oracle.grid_sweeps(want.mask, want.t, want.g, 150)
+    wout, werr = want.step(0)
+    np.testing.assert_array_equal(proc.core.state(), want.t)
+    np.testing.assert_array_equal(out, wout)
+    np.testing.assert_allclose(err, werr, rtol=1e-4)
+    equ = fpie_b200.EquProcessor("avg", "b200")
+    equ.reset(src, mask, tgt, (0, 0), (0, 0))
+    eout, _ = equ.step(150)
+    np.testing.assert_array_equal(eout, wout)
+
+
+def test_persistent_kernel_is_not_used_when_a_tile_shape_is_requested():
+    import fpie_b200
+    from fpie_b200 import synth
+
+    src, mask, tgt = synth.make_problem("circle", 128, 128, seed=1)
+    core = fpie_b200.GridSolver(8, 8, block_k=8, variant=24)
+    core.reset_from_images(src, mask, tgt, (0, 0), (0, 0), "max")
+    core.step(64)
+    assert not core.patch_info()["usable"] and core.patch_info()["launches"] == 0
