@@ -140,7 +140,42 @@ _PINNED = []
 # ---------------------------------------------------------------------------
 # CPU baseline (reference OpenMP core, or the C restatement when it is absent)
 # ---------------------------------------------------------------------------
-def cpu_baseline(work, src, mask, tgt, budget_s: float = 12.0, steps: int = 1):
+def ref_cuda_time(solver_kind, system, unknowns, iters):
+    """The reference's own CUDA backend (oracle/_ref/core_cuda: the unmodified sources compiled for sm_100a) on
+    this GPU, same system, its published tuning (`-z 256`, docs/benchmark.md:56; `--grid-x 2 --grid-y 128`,
+    :117), wall clock of `step(iters)` as the reference CLI times it (cli.py:46-61).  A throughput comparator
+    only: it updates in place without synchronisation (cuda/equ.cu:193-197, grid.cu:138-142), so its results
+    are not Jacobi.  None when the module is absent or no GPU is visible."""
+    import contextlib
+    import io
+
+    from oracle import c_oracle
+
+    try:
+        import torch
+
+        if not torch.cuda.is_available():
+            return None
+        core_cuda = c_oracle.load_reference_core("core_cuda")
+        if core_cuda is None:
+            return None
+        with contextlib.redirect_stdout(io.StringIO()):  # (its constructors print a device table)
+            ref = core_cuda.GridSolver(2, 128) if solver_kind == "grid" else core_cuda.EquSolver(256)
+        ref.reset(*system)
+        ref.step(10)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ref.step(iters)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        return {"value": unknowns * iters / dt / 1e9, "unit": "Gupd/s", "seconds": dt, "sweeps": iters,
+                "what": f"reference core_cuda.{'GridSolver(2, 128)' if solver_kind == 'grid' else 'EquSolver(256)'} "
+                        "(unmodified fpie/core/cuda built for sm_100a), same system, wall clock of step()"}
+    except Exception as exc:  # a comparator must never take the bench line down
+        return {"unavailable": f"{type(exc).__name__}: {exc}"}
+
+
+def cpu_baseline(work, src, mask, tgt, budget_s: float = 12.0, steps: int = 1, with_ref_cuda: bool = False):
     """Time the reference's CPU implementation on a bounded sample of the workload.
     Returns (dict for the JSON line, list of per-step seconds, sweeps per step)."""
     from oracle import c_oracle, np_oracle
@@ -148,9 +183,12 @@ def cpu_baseline(work, src, mask, tgt, budget_s: float = 12.0, steps: int = 1):
     cores = os.cpu_count() or 1
     core = c_oracle.load_reference_core("core_openmp")
     kind = "reference" if core is not None else "port"
+    ref_cuda = None
     if work["solver"] == "grid":
         m, t, g, _ = np_oracle.grid_system(src, mask, tgt, (0, 0), (0, 0), work["grad"])
         unknowns = int(m.sum())
+        if with_ref_cuda:
+            ref_cuda = ref_cuda_time("grid", (m.size, m, t, g), unknowns, min(work["iters"], 2000))
         if core is not None:
             solver = core.GridSolver(2, 16, cores)  # published tuning, docs/benchmark.md:111
             solver.reset(m.size, m, t, g)
@@ -163,6 +201,8 @@ def cpu_baseline(work, src, mask, tgt, budget_s: float = 12.0, steps: int = 1):
     else:
         n, A, X, B, _ = np_oracle.equ_system(src, mask, tgt, (0, 0), (0, 0), work["grad"])
         unknowns = n - 1
+        if with_ref_cuda:
+            ref_cuda = ref_cuda_time("equ", (n, A, X, B), unknowns, min(work["iters"], 2000))
         # the reference's OpenMP EquSolver is red-black Gauss-Seidel (openmp/equ.cc:107-118): same
         # memory traffic per sweep, so it is the throughput baseline; the Jacobi port checks results.
         if core is not None:
@@ -194,6 +234,8 @@ def cpu_baseline(work, src, mask, tgt, budget_s: float = 12.0, steps: int = 1):
         "sample": f"{sweeps} of {work['iters']} sweeps on the full {work['size']}^2 {work['mask']} workload "
         f"({'core_openmp from oracle/_ref' if kind == 'reference' else 'oracle/jacobi_oracle.c'}, {cores} threads)",
     }
+    if with_ref_cuda:
+        info["_ref_cuda"] = ref_cuda
     return info, times, sweeps, unknowns
 
 
@@ -370,14 +412,15 @@ def run_single(args, work, name):
         "api": f"fpie_b200.{Proc.__name__}.reset(src, mask, tgt) + step({iters}) on pinned host uint8 images",
     }
 
-    base = None
+    base = ref_cuda = None
     if not args.no_cpu_baseline:
         if is_batch:  # one patch after the other on the host, as the reference GUI does; sample = first patches
             w1 = dict(work, solver="grid")
-            base, _, _, _ = cpu_baseline(w1, src[0], mask[0], tgt[0], budget_s=args.cpu_budget)
+            base, _, _, _ = cpu_baseline(w1, src[0], mask[0], tgt[0], budget_s=args.cpu_budget, with_ref_cuda=True)
             base["sample"] = "patch 0 of the batch: " + base["sample"]
         else:
-            base, _, _, _ = cpu_baseline(work, src, mask, tgt, budget_s=args.cpu_budget)
+            base, _, _, _ = cpu_baseline(work, src, mask, tgt, budget_s=args.cpu_budget, with_ref_cuda=True)
+        ref_cuda = base.pop("_ref_cuda", None)
 
     line = {
         "metric": "jacobi_gupd_per_s",
@@ -410,6 +453,9 @@ def run_single(args, work, name):
         },
         "roofline": roofline,
         "cpu_baseline": base,
+        # the reference's existing CUDA backend on the same GPU, same run (north star: "... and the reference's
+        # existing CUDA backend"); for the batch workload: one patch, as the reference GUI would solve it
+        "ref_cuda": ref_cuda,
         "e2e": e2e,
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
@@ -625,14 +671,15 @@ def run_band(args, work, name):
     if rank == 0 and not args.no_scaling_reference:
         ref1 = single_gpu_reference(work, n, m, iters, dev, args.block_k)
     dist.barrier()
-    base = None
+    base = ref_cuda = None
     if rank == 0 and not args.no_cpu_baseline:
         # the reference's OpenMP core overflows int32 offsets at 3*N*M >= 2^31 (base_solver.h:114-117): the host
         # baseline runs the same kind of problem at 8192^2 (per-pixel throughput is size-independent there)
         w8 = dict(work, size=8192)
         s8, m8, t8, _ = slab_images(w8, 0, 8192, 8192, 8192)
-        base, _, _, _ = cpu_baseline(w8, s8, m8, t8, budget_s=args.cpu_budget)
+        base, _, _, _ = cpu_baseline(w8, s8, m8, t8, budget_s=args.cpu_budget, with_ref_cuda=True)
         base["sample"] += " -- 8192^2 instead of 32768^2: the reference core cannot index the full problem"
+        ref_cuda = base.pop("_ref_cuda", None)
 
     k = info["block_k"]
     peak, peak_src = measured_peak()
@@ -682,6 +729,7 @@ def run_band(args, work, name):
                         "(ncu, one GPU, profiles/)",
             },
             "cpu_baseline": base,
+            "ref_cuda": ref_cuda,  # (one GPU, 8192^2: the reference has no multi-GPU path)
             "e2e": {"value": unknowns * iters / e2e_s / 1e9, "unit": "Gupd/s", "h2d_bytes_per_step": int(h2d.item()),
                     "d2h_bytes_per_step": int(d2h.item()), "ms_per_step": e2e_s * 1e3,
                     "reset_ms": float(np.mean(e2e_reset)) * 1e3,
