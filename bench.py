@@ -146,9 +146,6 @@ def ref_cuda_time(solver_kind, system, unknowns, iters):
     :117), wall clock of `step(iters)` as the reference CLI times it (cli.py:46-61).  A throughput comparator
     only: it updates in place without synchronisation (cuda/equ.cu:193-197, grid.cu:138-142), so its results
     are not Jacobi.  None when the module is absent or no GPU is visible."""
-    import contextlib
-    import io
-
     from oracle import c_oracle
 
     try:
@@ -159,8 +156,17 @@ def ref_cuda_time(solver_kind, system, unknowns, iters):
         core_cuda = c_oracle.load_reference_core("core_cuda")
         if core_cuda is None:
             return None
-        with contextlib.redirect_stdout(io.StringIO()):  # (its constructors print a device table)
+        # its constructors printf a device table (fpie/core/cuda/utils.cu:5-22) -- on file descriptor 1, where
+        # this script owes exactly one JSON line
+        sys.stdout.flush()
+        saved, devnull = os.dup(1), os.open(os.devnull, os.O_WRONLY)
+        try:
+            os.dup2(devnull, 1)
             ref = core_cuda.GridSolver(2, 128) if solver_kind == "grid" else core_cuda.EquSolver(256)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+            os.close(devnull)
         ref.reset(*system)
         ref.step(10)
         torch.cuda.synchronize()
@@ -629,6 +635,24 @@ def run_band(args, work, name):
             times.append(float(t.item()))
     launches = torch.tensor([core.info()["launches"] - launches0], device="cuda")
     dist.all_reduce(launches)
+    if args.trace_intervals > 0 and args.transport == "p2p":
+        # an untimed extra step with CUDA events around every phase of the first intervals (csrc/halo.cu tags)
+        torch.cuda.synchronize()
+        dist.barrier()
+        core.halo_trace_begin(args.trace_intervals)
+        device_step()
+        trace = core.halo_trace()
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"band_trace_rank{rank}.json"), "w") as f:
+            json.dump({"rank": rank, "world": world, "halo": halo, "block_k": core.info()["block_k"],
+                       "tags": {"1": "before edge tiles (single-pass interval)", "2": "after edge tiles of the last pass",
+                                "3": "after interior tiles of the last pass", "4": "before interior tiles of the first pass",
+                                "5": "after interior tiles of the first pass", "6": "after edge tiles of the first pass",
+                                "10": "halo stream: peer copies start", "11": "halo stream: peer copies + flags issued done",
+                                "20": "solver stream: wait for the neighbours' rows starts",
+                                "21": "solver stream: rows received and copied into the halo"},
+                       "events_ms": trace}, f)
+        dist.barrier()
     ms_per_step = float(np.mean(times))
     value = unknowns * iters / (ms_per_step * 1e-3) / 1e9
 
@@ -762,6 +786,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
                     help="row bands: halo rows by copy-engine peer copies behind the C ABI (p2p) or NCCL send/recv")
+    ap.add_argument("--trace-intervals", type=int, default=0,
+                    help="row bands: record a phase timeline of the first N exchange intervals of one extra step into "
+                         "gpurun_out/band_trace_rank<r>.json (CUDA events; the extra step is not timed)")
     ap.add_argument("--no-parity", action="store_true", help="row bands: skip the in-run sharded-vs-single-GPU check")
     ap.add_argument("--no-scaling-reference", action="store_true",
                     help="row bands: skip the in-run single-GPU measurement of the same workload")

@@ -13,6 +13,8 @@
 #include <cstring>
 #include <vector>
 
+#include <cstdlib>
+
 #include "equ_solver.cuh"
 #include "prep.cuh"
 
@@ -173,14 +175,21 @@ __global__ void __launch_bounds__(1024)
 equ_sweep_lr_kernel(long long N, long long pitch, const int2 *__restrict__ UD, const float *__restrict__ B,
                     const float *__restrict__ xin, float *__restrict__ xout) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  // programmatic dependent launch: the next sweep may be scheduled now; the table and B are not written by
+  // sweeps and are fetched before this grid waits for the previous sweep's X
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (i >= N) return;
   const int2 ud = UD[i];
   const int up = ud.x & 0x7fffffff, dn = ud.y & 0x7fffffff;
   const long long lf = (ud.x < 0) ? i - 1 : 0, rt = (ud.y < 0) ? i + 1 : 0;
+  float b[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) b[ch] = B[ch * pitch + i];
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
     const float *x = xin + ch * pitch;
-    float s = __fadd_rn(B[ch * pitch + i], x[up]);
+    float s = __fadd_rn(b[ch], x[up]);
     s = __fadd_rn(s, x[dn]);
     s = __fadd_rn(s, x[lf]);
     s = __fadd_rn(s, x[rt]);
@@ -193,12 +202,17 @@ __global__ void __launch_bounds__(1024)
 equ_sweep_kernel(long long N, long long pitch, const int4 *__restrict__ A, const float *__restrict__ B,
                  const float *__restrict__ xin, float *__restrict__ xout) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // (see equ_sweep_lr_kernel)
   if (i >= N) return;
   const int4 a = A[i];
+  float b[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) b[ch] = B[ch * pitch + i];
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
     const float *x = xin + ch * pitch;
-    float s = __fadd_rn(B[ch * pitch + i], x[a.x]);
+    float s = __fadd_rn(b[ch], x[a.x]);
     s = __fadd_rn(s, x[a.y]);
     s = __fadd_rn(s, x[a.z]);
     s = __fadd_rn(s, x[a.w]);
@@ -364,6 +378,8 @@ equ_paste_kernel(long long K, long long pitch, const float *__restrict__ x, cons
 static int blocks_for(long long work, int threads) { return (int)ceil_div(work, threads); }
 
 EquSolver::EquSolver(int device, cudaStream_t stream, int block_size) : device_(device), stream_(stream) {
+  const char *no_graph = getenv("FPIE_B200_NO_GRAPH");
+  graph_off_ = no_graph && no_graph[0] && no_graph[0] != '0';
   int count = 0;
   CUDA_CHECK(cudaGetDeviceCount(&count));
   FPIE_REQUIRE(device >= 0 && device < count, "fpie_b200: no such CUDA device");
@@ -389,6 +405,8 @@ EquSolver::~EquSolver() {
   int prev = -1;  // (see GridSolver::~GridSolver)
   cudaGetDevice(&prev);
   cudaSetDevice(device_);
+  drop_graphs();
+  if (cap_stream_) cudaStreamDestroy(cap_stream_);
   if (host_err_) cudaFreeHost(host_err_);
   if (host_flag_) cudaFreeHost(host_flag_);
   if (prev >= 0 && prev != device_) cudaSetDevice(prev);
@@ -461,6 +479,7 @@ void EquSolver::partition(int n, int m, const int32_t *mask, int64_t mask_rs, in
 }
 
 void EquSolver::allocate(int64_t N) {
+  drop_graphs();  // (they hold the old buffers and sizes)
   N_ = N;
   pitch_ = round_up(N, 32);
   A_.resize((size_t)N);
@@ -634,17 +653,72 @@ void EquSolver::sweeps_async(int iters) {
     tiled_dirty_ = tiled_dirty_ || iters > 0;
     return;
   }
-  for (int i = 0; i < iters; ++i) {
-    if (structured_)
-      equ_sweep_lr_kernel<<<blocks_for(N_, block_), block_, 0, stream_>>>(N_, pitch_, ud_.ptr, B_.ptr, X_[cur_].ptr,
-                                                                         X_[cur_ ^ 1].ptr);
-    else
-      equ_sweep_kernel<<<blocks_for(N_, block_), block_, 0, stream_>>>(N_, pitch_, A_.ptr, B_.ptr, X_[cur_].ptr,
-                                                                      X_[cur_ ^ 1].ptr);
-    cur_ ^= 1;
+  // One launch per sweep, chained by programmatic dependent launch (the next sweep's CTAs are resident and have
+  // their table rows and B in registers when the previous sweep drains); long runs replay a captured graph of
+  // kGraphSweeps sweeps, so that an L2-resident system (config 1: a sweep is a few microseconds) is not bound by
+  // the host's launch rate.
+  auto one_sweep = [&](cudaStream_t st, int &cur) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks_for(N_, block_));
+    cfg.blockDim = dim3(block_);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const float *xin = X_[cur].ptr;
+    float *xout = X_[cur ^ 1].ptr;
+    const float *b = B_.ptr;
+    if (structured_) {
+      const int2 *ud = ud_.ptr;
+      CUDA_CHECK(cudaLaunchKernelEx(&cfg, equ_sweep_lr_kernel, (long long)N_, (long long)pitch_, ud, b, xin, xout));
+    } else {
+      const int4 *a = A_.ptr;
+      CUDA_CHECK(cudaLaunchKernelEx(&cfg, equ_sweep_kernel, (long long)N_, (long long)pitch_, a, b, xin, xout));
+    }
+    cur ^= 1;
+  };
+  int left = iters;
+  if (!graph_off_ && left >= 2 * kGraphSweeps) {
+    if (!graph_warm_) {  // (first launches outside a capture: lazy kernel loading)
+      for (int i = 0; i < 2; ++i) one_sweep(stream_, cur_);
+      left -= 2;
+      graph_warm_ = true;
+    }
+    if (!graph_[cur_]) {
+      if (!cap_stream_) CUDA_CHECK(cudaStreamCreateWithFlags(&cap_stream_, cudaStreamNonBlocking));
+      int c = cur_;
+      CUDA_CHECK(cudaStreamBeginCapture(cap_stream_, cudaStreamCaptureModeThreadLocal));
+      cudaGraph_t captured = nullptr;
+      try {
+        for (int i = 0; i < kGraphSweeps; ++i) one_sweep(cap_stream_, c);
+      } catch (...) {
+        cudaStreamEndCapture(cap_stream_, &captured);
+        if (captured) cudaGraphDestroy(captured);
+        throw;
+      }
+      CUDA_CHECK(cudaStreamEndCapture(cap_stream_, &captured));
+      const cudaError_t rc = cudaGraphInstantiate(&graph_[cur_], captured, 0);
+      cudaGraphDestroy(captured);
+      CUDA_CHECK(rc);
+    }
+    while (left >= kGraphSweeps) {  // (an even number of sweeps: the graph starts and ends on the same buffer)
+      CUDA_CHECK(cudaGraphLaunch(graph_[cur_], stream_));
+      left -= kGraphSweeps;
+    }
   }
+  for (; left > 0; --left) one_sweep(stream_, cur_);
   stats_.launches += iters;
   CUDA_CHECK(cudaGetLastError());
+}
+
+void EquSolver::drop_graphs() {
+  for (auto &gx : graph_) {
+    if (gx) cudaGraphExecDestroy(gx);
+    gx = nullptr;
+  }
+  graph_warm_ = false;
 }
 
 void EquSolver::finish_async() {

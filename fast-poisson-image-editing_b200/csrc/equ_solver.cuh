@@ -49,6 +49,7 @@ class EquSolver {
   void compact_tables();
   void try_promote(int n, int m);
   void pull_tiled_state();
+  void drop_graphs();
 
   int device_;
   cudaStream_t stream_;
@@ -85,6 +86,11 @@ class EquSolver {
   int crop_n_ = 0, crop_m_ = 0;
   DeviceBuffer<int32_t> pix_;     // [K] linear crop index of unknown i+1
   DeviceBuffer<uint8_t> canvas_;  // [crop_n, crop_m, 3] target pixels of the crop
+  // CUDA graph of kGraphSweeps gather sweeps per starting buffer (long runs on small systems)
+  static constexpr int kGraphSweeps = 64;
+  cudaStream_t cap_stream_ = nullptr;
+  cudaGraphExec_t graph_[2] = {nullptr, nullptr};
+  bool graph_off_ = false, graph_warm_ = false;
   EquStats stats_;
 };
 

@@ -494,7 +494,20 @@ __device__ __forceinline__ float resid_term(float t, float hq, float up, float d
   return fabsf(v);
 }
 
+// the EquSolver's expression of the same residual, |((((B + U) + D) + L) + R) - 4 X| (np_solver.py:42-50,
+// equ.cu equ_residual_kernel), on the grid embedding of an Equ system (B = 4 hq exactly, absent neighbours
+// hold the constant 0): rounds differently from the grid expression once the residual is rounding noise
+__device__ __forceinline__ float resid_term_equ(float t, float hq, float up, float dn, float lf, float rt) {
+  float s = __fadd_rn(__fmul_rn(4.0f, hq), up);
+  s = __fadd_rn(s, dn);
+  s = __fadd_rn(s, lf);
+  s = __fadd_rn(s, rt);
+  s = __fsub_rn(s, __fmul_rn(4.0f, t));
+  return fabsf(s);
+}
+
 // grid: (blocks over rows x groups, plane).  err[plane % 3] accumulates in double.
+template <bool EQU>
 __global__ void __launch_bounds__(256)
 grid_residual_kernel(PlaneGeom g, BatchMap bm, int row_lo, int row_hi, const uint32_t *__restrict__ bits,
                      const float *__restrict__ x, const float *__restrict__ hq, double *__restrict__ err) {
@@ -510,10 +523,17 @@ grid_residual_kernel(PlaneGeom g, BatchMap bm, int row_lo, int row_hi, const uin
       const long long off = (long long)p * g.plane + (long long)(r + g.padr) * g.pitch + pc;
       const float4 c = ld4(x + off), u = ld4(x + off - g.pitch), d = ld4(x + off + g.pitch), h = ld4(hq + off);
       const float lf = x[off - 1], rt = x[off + 4];
-      if (nib & 1u) acc += resid_term(c.x, h.x, u.x, d.x, lf, c.y);
-      if (nib & 2u) acc += resid_term(c.y, h.y, u.y, d.y, c.x, c.z);
-      if (nib & 4u) acc += resid_term(c.z, h.z, u.z, d.z, c.y, c.w);
-      if (nib & 8u) acc += resid_term(c.w, h.w, u.w, d.w, c.z, rt);
+      if (EQU) {
+        if (nib & 1u) acc += resid_term_equ(c.x, h.x, u.x, d.x, lf, c.y);
+        if (nib & 2u) acc += resid_term_equ(c.y, h.y, u.y, d.y, c.x, c.z);
+        if (nib & 4u) acc += resid_term_equ(c.z, h.z, u.z, d.z, c.y, c.w);
+        if (nib & 8u) acc += resid_term_equ(c.w, h.w, u.w, d.w, c.z, rt);
+      } else {
+        if (nib & 1u) acc += resid_term(c.x, h.x, u.x, d.x, lf, c.y);
+        if (nib & 2u) acc += resid_term(c.y, h.y, u.y, d.y, c.x, c.z);
+        if (nib & 4u) acc += resid_term(c.z, h.z, u.z, d.z, c.y, c.w);
+        if (nib & 8u) acc += resid_term(c.w, h.w, u.w, d.w, c.z, rt);
+      }
     }
   }
   if (bm.batch > 0) {
@@ -827,6 +847,7 @@ void GridSolver::reset(int n, int m, const int32_t *mask, int64_t mask_rs, int64
   FPIE_REQUIRE(mask_cs == 1 && mask_rs >= m, "GridSolver.reset: mask rows must be contiguous (column stride 1)");
   DeviceGuard guard(device_);
   ready_ = false;
+  resid_equ_ = false;
   zeroed_ = PlaneGeom{};
   batch_ = BatchMap{0, 0, 0, 0};
   layout(n, m);
@@ -901,6 +922,7 @@ void GridSolver::reset_batch(const uint8_t *src, const uint8_t *mask, const uint
 void GridSolver::reset_from_equ(const EquEmbed &e) {
   DeviceGuard guard(device_);
   ready_ = false;
+  resid_equ_ = false;
   zeroed_ = PlaneGeom{};
   batch_ = BatchMap{0, 0, 0, 0};
   layout(e.n, e.m);
@@ -934,6 +956,7 @@ void GridSolver::export_to_equ(const EquEmbed &e) {
 void GridSolver::build_from_upload() {
   const BlendImages &b = upload_.images();
   FPIE_REQUIRE(!(equ_form_ && b.batch > 0), "the EquSolver formulation is not available for batched patches");
+  resid_equ_ = equ_form_;
   layout(b.n, b.m);
   const PlaneGeom &g = geom_;
   for (auto &buf : x_) buf.resize((size_t)g.plane * 3);
@@ -1565,7 +1588,8 @@ void GridSolver::pass_async(int nsweeps, int part) {
 void GridSolver::preload_kernels() {
   DeviceGuard guard(device_);
   cudaFuncAttributes attr;
-  CUDA_CHECK(cudaFuncGetAttributes(&attr, grid_residual_kernel));
+  CUDA_CHECK(cudaFuncGetAttributes(&attr, grid_residual_kernel<false>));
+  CUDA_CHECK(cudaFuncGetAttributes(&attr, grid_residual_kernel<true>));
   CUDA_CHECK(cudaFuncGetAttributes(&attr, grid_to_u8_kernel));
   CUDA_CHECK(cudaFuncGetAttributes(&attr, planes_to_aos_kernel));
   CUDA_CHECK(cudaFuncGetAttributes(&attr, grid_sweep1_kernel));
@@ -1615,8 +1639,12 @@ void GridSolver::finish_async() {
   const long long work = (long long)(win_hi_ - win_lo_) * g.groups;
   if (work > 0 && stats_.unknowns > 0) {
     dim3 grid(blocks_for(work, 256), 3);
-    grid_residual_kernel<<<grid, 256, 0, stream_>>>(g, batch_, win_lo_, win_hi_, bits_.ptr, x_[cur_].ptr, hq_.ptr,
-                                                    batch_.batch > 0 ? batch_err_.ptr : err_.ptr);
+    if (resid_equ_)  // (an image-level reset in the EquSolver's formulation: the EquSolver's residual expression too)
+      grid_residual_kernel<true><<<grid, 256, 0, stream_>>>(g, batch_, win_lo_, win_hi_, bits_.ptr, x_[cur_].ptr, hq_.ptr,
+                                                            batch_.batch > 0 ? batch_err_.ptr : err_.ptr);
+    else
+      grid_residual_kernel<false><<<grid, 256, 0, stream_>>>(g, batch_, win_lo_, win_hi_, bits_.ptr, x_[cur_].ptr, hq_.ptr,
+                                                             batch_.batch > 0 ? batch_err_.ptr : err_.ptr);
     CUDA_CHECK(cudaGetLastError());
     stats_.launches += 1;
   }

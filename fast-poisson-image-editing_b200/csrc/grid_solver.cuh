@@ -120,6 +120,7 @@ class GridSolver {
   int halo_x_;
   int variant_;
   bool equ_form_ = false;
+  bool resid_equ_ = false;  // the loaded state is in the EquSolver's formulation: its residual expression applies
   bool auto_tune_ = false;  // tile shape chosen at reset
   bool auto_k_ = false;     // blocking depth chosen at reset
   int sm_count_ = 0;

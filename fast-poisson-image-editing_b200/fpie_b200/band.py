@@ -228,13 +228,28 @@ class BandGridSolver:
             self.core.finish_async()
             lo, hi = self.plan.local_band
             if hasattr(self.core, "fetch_rows"):  # download the band, not the neighbours' halo rows
-                img, err = self.core.fetch_rows(lo, hi)
+                img, err = self.core.fetch_rows(lo, hi, self._band_buffer(hi - lo))
             else:
                 slab_img, err = self.core.fetch()
                 img = slab_img[lo:hi]
         total = torch.tensor(np.asarray(err, np.float64), device=self._reduce_device())
         self.dist.all_reduce(total, group=self.group)
         return img, total.cpu().numpy().astype(np.float32)
+
+    def _band_buffer(self, rows: int):
+        """Page-locked landing buffer for the band's uint8 image (None = let the core allocate a pageable one).
+        Large bands only -- hundreds of megabytes per step at PCIe speed instead of pageable speed; the buffer is
+        recycled, so ``step`` returns an array that stays valid until the next ``step`` of this solver."""
+        shape = getattr(self.core, "shape", None)
+        if shape is None or not hasattr(self.core, "pinned_empty"):
+            return None
+        want = (rows, shape[1], 3)
+        if int(np.prod(want)) < (32 << 20):
+            return None
+        buf = getattr(self, "_band_img", None)
+        if buf is None or buf.shape != want:
+            buf = self._band_img = self.core.pinned_empty(want, np.uint8)
+        return buf
 
     def band_state(self) -> np.ndarray:
         lo, hi = self.plan.local_band
@@ -554,6 +569,16 @@ class CudaBandCore:
 
     def fetch_rows(self, lo, hi, img=None):
         return self.solver.fetch_rows(lo, hi, img)
+
+    @property
+    def shape(self):
+        return self.solver.shape
+
+    @staticmethod
+    def pinned_empty(shape, dtype):
+        from . import _lib
+
+        return _lib.pinned_empty(shape, dtype)
 
     def state(self):
         return self.solver.state()

@@ -376,3 +376,36 @@ def test_promotion_is_refused_when_the_system_does_not_match_the_mask(golden):
     s.partition(np.ascontiguousarray(crop[:, ::-1]))
     s.step(3)
     np.testing.assert_array_equal(s.state(), np_oracle.equ_sweeps(A, X, B, 9))
+
+
+@pytest.mark.parametrize("generic", [False, True])
+def test_gather_long_runs_replay_a_cuda_graph(generic, monkeypatch):
+    """BASELINE config 1 (1026^2 square, 1 048 576 unknowns, L2-resident) on the index-mapped gather path:
+    long runs replay a captured graph of 64 sweeps chained by programmatic dependent launch.  Same bits as the C
+    restatement, as the same run without graphs, and across repeated step / reset calls."""
+    import fpie_b200
+    from fpie_b200 import synth
+
+    src, mask, tgt = synth.make_problem("square", 1026, 1026, seed=0)
+    n, A, X, B, _ = np_oracle.equ_system(src, mask, tgt, (0, 0), (0, 0), "max")
+    if generic:  # a legal relabelling (ids reversed) defeats the compact table: the generic int4 kernel
+        perm = np.concatenate([[0], np.arange(n - 1, 0, -1)]).astype(np.int32)
+        inv = np.empty_like(perm)
+        inv[perm] = np.arange(n, dtype=np.int32)
+        A, X, B = inv[A[perm]], X[perm], B[perm]
+    s = fpie_b200.EquSolver(256, mode="gather")
+    s.reset(n, A, X, B)
+    assert s.info()["path"] == ("gather-int4" if generic else "gather-compact")
+    s.step(150)  # warm launches + two graph replays + a tail
+    img, err = s.step(211)
+    want = c_oracle.equ_sweeps(A, X, B, 361)
+    np.testing.assert_array_equal(s.state(), want)
+    np.testing.assert_array_equal(img, c_oracle.clip_u8(want))
+    s.reset(n, A, X, B)  # buffers may move: the graphs must be rebuilt, not replayed
+    s.step(361)
+    np.testing.assert_array_equal(s.state(), want)
+    monkeypatch.setenv("FPIE_B200_NO_GRAPH", "1")
+    plain = fpie_b200.EquSolver(256, mode="gather")
+    plain.reset(n, A, X, B)
+    plain.step(361)
+    np.testing.assert_array_equal(plain.state(), want)

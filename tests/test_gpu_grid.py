@@ -415,3 +415,50 @@ def test_info_reports_the_kernel_configuration():
     s.reset(mask.size, mask, tgt, grad)
     info = s.info()
     assert (info["variant"], info["rows_per_thread"], info["warps"], info["ctas_per_sm"], info["block_k"]) == (24, 21, 8, 1, 8)
+
+
+def test_config2_full_size_full_sweeps_vs_reference_openmp_and_c_oracle():
+    """BASELINE config 2 at full size and full length (4096^2 circle, grad max, 5000 sweeps), SURVEY.md 8(d):
+    fp32 state bit-exact against the C restatement of np_solver (numpy add order), and -- when oracle/_ref
+    carries it -- uint8 within 1 and err within 1e-4 of the reference's own compiled OpenMP GridSolver
+    (true Jacobi in another add order, openmp/grid.cc:29-44).  About a minute of host time."""
+    import fpie_b200
+    from fpie_b200 import synth
+
+    src, mask, tgt = synth.make_problem("circle", 4096, 4096, seed=0)
+    proc = fpie_b200.GridProcessor("max", "b200")
+    proc.reset(src, mask, tgt, (0, 0), (0, 0))
+    out, err = proc.step(5000)
+    m, t, g, box = np_oracle.grid_system(src, mask, tgt, (0, 0), (0, 0), "max")
+    want = c_oracle.grid_sweeps(m, t, g, 5000)
+    assert np.abs(proc.core.state() - want).max() <= STATE_TOL
+    np.testing.assert_array_equal(proc.core.state(), want)
+    np.testing.assert_array_equal(out[box[0] : box[1], box[2] : box[3]], c_oracle.clip_u8(want))
+    _check_err(err, c_oracle.grid_residual(m, want, g)[1])
+    core = c_oracle.load_reference_core("core_openmp")
+    if core is None:
+        return
+    import os
+
+    ref = core.GridSolver(2, 16, os.cpu_count() or 1)  # published tuning, docs/benchmark.md:111
+    ref.reset(m.size, m, t, g)
+    rimg, rerr = ref.step(5000)
+    mine = out[box[0] : box[1], box[2] : box[3]]
+    assert int(np.abs(mine.astype(np.int16) - rimg.astype(np.int16)).max()) <= 1
+    # err: the OpenMP core adds its 13 M terms per channel into ONE fp32 accumulator, serially
+    # (openmp/grid.cc:66-72); past 2^24 every addition rounds to a multiple of 2 and the total drifts by more
+    # than a percent from the true sum (this backend's err is within 2e-6 of the fp64 sum, checked above; numpy's
+    # pairwise np.sum is accurate too).  So: the reference's figure within a few percent, and the reference's
+    # ARITHMETIC -- same expression, same serial fp32 accumulation, emulated on this backend's state -- within the stated 1e-4 (4e-7 in practice).
+    np.testing.assert_allclose(err, rerr, rtol=5e-2)
+    t64, g64 = proc.core.state().astype(np.float64), g.astype(np.float64)
+    f32 = np.float32
+    sums = (g[1:-1, 1:-1] + proc.core.state()[:-2, 1:-1]).astype(f32)  # float adds, as the C++ expression evaluates
+    sums = (sums + proc.core.state()[1:-1, :-2]).astype(f32)
+    sums = (sums + proc.core.state()[1:-1, 2:]).astype(f32)
+    sums = (sums + proc.core.state()[2:, 1:-1]).astype(f32)
+    terms = np.abs(sums.astype(np.float64) - t64[1:-1, 1:-1] * 4.0).astype(f32)  # ... minus a double product
+    terms[m[1:-1, 1:-1] == 0] = 0
+    del t64, g64, sums
+    serial = np.array([np.cumsum(terms[..., c].ravel(), dtype=f32)[-1] for c in range(3)])
+    np.testing.assert_allclose(serial, rerr, rtol=ERR_RTOL)
