@@ -459,6 +459,7 @@ grid_sweepk_pipe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
 }  // namespace fpie
 #include "grid_pair.cuh"
 #include "patch.cuh"
+#include "grid_cluster.cuh"
 namespace fpie {
 
 // Classify the tile grid: flag bit0 = some masked pixel in the stored (inner)
@@ -736,6 +737,7 @@ GridSolver::GridSolver(int device, cudaStream_t stream, int block_k, int variant
   // FPIE_B200_PATCH_ROWS=4|8 overrides the rows per thread
   const char *patch = getenv("FPIE_B200_PATCH");
   patch_off_ = patch && patch[0] == '0';
+  patch_force_ = patch && patch[0] == '2';  // FPIE_B200_PATCH=2: also for fewer than 12 items (single images)
   const char *prow = getenv("FPIE_B200_PATCH_ROWS");
   patch_rows_ = prow ? atoi(prow) : 0;
   if (patch_rows_ != 4 && patch_rows_ != 8) patch_rows_ = 0;
@@ -1237,9 +1239,57 @@ void launch_pair(const SweepArgs &a) {
     launch_pair_h<R, NW, OCC, false>(a);
 }
 
+template <int R, int NW, int OCC, bool H16>
+void launch_cluster_h(const SweepArgs &a, int cluster) {
+  auto kernel = grid_sweepk_cluster_kernel<R, NW, OCC, H16>;
+  constexpr size_t smem = ClusterSmem<R, NW, H16>::TOTAL;
+  static int configured_device = -1;
+  int dev = 0;
+  CUDA_CHECK(cudaGetDevice(&dev));
+  if (configured_device != dev) {
+    CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured_device = dev;
+  }
+  if (a.load_only) return;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(NW * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = a.stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // clusters the device holds at once (a cluster lives inside one GPC): asked once per cluster size
+  static int max_clusters[9] = {0};
+  if (!max_clusters[cluster]) {
+    cfg.gridDim = dim3(cluster * a.grid * OCC);
+    CUDA_CHECK(cudaOccupancyMaxActiveClusters(&max_clusters[cluster], kernel, &cfg));
+    FPIE_REQUIRE(max_clusters[cluster] > 0, "the cluster kernel does not fit this device");
+  }
+  const int clusters = std::min(a.ntiles, max_clusters[cluster]);
+  cfg.gridDim = dim3(clusters * cluster);
+  cfg.numAttrs = (a.ntiles >= a.grid / cluster) ? 2 : 1;
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, *a.tm_x, *a.tm_h, *a.tm_m, a.g, a.xout, a.tiles, a.ntiles, a.nsweeps,
+                                a.halo_y, a.halo_x, a.reverse));
+}
+
+template <int R, int NW, int OCC>
+void launch_cluster(const SweepArgs &a, int cluster) {
+  if (a.h16)
+    launch_cluster_h<R, NW, OCC, true>(a, cluster);
+  else
+    launch_cluster_h<R, NW, OCC, false>(a, cluster);
+}
+
 struct VariantInfo {
   int rows, warps, occ;
   bool pipe;
+  int cluster = 1;
 };
 
 // kernel variants (fpie_b200_grid_create `variant`): register-tile shape
@@ -1261,6 +1311,11 @@ VariantInfo variant_info(int v) {
     case 40: return {22, 8, 1, true};
     case 41: return {20, 8, 1, true};
     case 42: return {20, 4, 2, true};
+    // cluster kernels: `cluster` CTAs of 4 warps x 21 rows stacked on one tile, two CTAs per SM
+    case 50: return {21, 4, 2, true, 2};
+    case 51: return {21, 4, 2, true, 4};
+    case 52: return {21, 4, 2, true, 3};
+    case 53: return {14, 4, 3, true, 4};
     case 43: return {14, 12, 1, true};
     case 44: return {10, 16, 1, true};
 #ifdef FPIE_ALL_VARIANTS
@@ -1297,6 +1352,10 @@ static void launch_variant(int variant, const SweepArgs &a) {
     case 40: launch_pair<11, 8, 1>(a); break;
     case 41: launch_pair<10, 8, 1>(a); break;
     case 42: launch_pair<10, 4, 2>(a); break;
+    case 50: launch_cluster<21, 4, 2>(a, 2); break;
+    case 51: launch_cluster<21, 4, 2>(a, 4); break;
+    case 52: launch_cluster<21, 4, 2>(a, 3); break;
+    case 53: launch_cluster<14, 4, 3>(a, 4); break;
     case 43: launch_pair<7, 12, 1>(a); break;
     case 44: launch_pair<5, 16, 1>(a); break;
 #ifdef FPIE_ALL_VARIANTS
@@ -1334,16 +1393,16 @@ void GridSolver::config(int *variant, int *rows, int *warps, int *occ) const {
 
 TileShape GridSolver::shape_for(int variant) {
   const VariantInfo v = variant_info(variant);
-  return {v.rows, v.warps};
+  return {v.rows, v.warps, v.cluster};
 }
 
 void GridSolver::make_tensor_maps() {
   const PlaneGeom &g = geom_;
   for (int i = 0; i < 2; ++i)
-    tm_x_[i] = make_plane_tensor_map(x_[i].ptr, g.pitch, g.rows, 3, g.plane, TILE_W, shape_.tile_h());
-  tm_h_ = make_plane_tensor_map(hq_.ptr, g.pitch, g.rows, 3, g.plane, TILE_W, shape_.tile_h());
-  tm_h16_ = make_plane_tensor_map(hq16_.ptr, g.pitch, g.rows, 3, g.plane, TILE_W + 8, shape_.tile_h(), true);
-  tm_m_ = make_mask_tensor_map(bits_.ptr, g.wpitch, g.rows, MASK_BOX_WORDS, shape_.tile_h());
+    tm_x_[i] = make_plane_tensor_map(x_[i].ptr, g.pitch, g.rows, 3, g.plane, TILE_W, shape_.box_h());
+  tm_h_ = make_plane_tensor_map(hq_.ptr, g.pitch, g.rows, 3, g.plane, TILE_W, shape_.box_h());
+  tm_h16_ = make_plane_tensor_map(hq16_.ptr, g.pitch, g.rows, 3, g.plane, TILE_W + 8, shape_.box_h(), true);
+  tm_m_ = make_mask_tensor_map(bits_.ptr, g.wpitch, g.rows, MASK_BOX_WORDS, shape_.box_h());
 }
 
 namespace {
@@ -1402,8 +1461,15 @@ bool GridSolver::patch_shape(int *rows_per_thread, int *cols_per_thread, int *cl
   const bool single = batch_.batch == 0;
   const int ph = single ? geom_.n : batch_.ph, pw = single ? geom_.m : batch_.pw;
   if (pw > 256 || ph > 512) return false;
+  // Measured on B200 (tools/patch_bench.py, profiles/r02_patch_bench.json): a sweep of the persistent kernel is
+  // bound by the per-sweep hand-over between the CTAs of a cluster (0.6-0.75 us), not by arithmetic, so it pays
+  // once enough (patch, plane) items run side by side: 12 patches of 256^2 -> 530 vs 445 Gupd/s for the mosaic
+  // through the tiled kernel, 512 patches -> 948 vs 807; ONE 256^2 image is faster on the tiled kernel (125 vs 107).
+  const int items = (single ? 1 : batch_.batch) * 3;
+  if (!patch_force_ && items < 12) return false;
   const int cpt = pw <= 128 ? 4 : 8;
-  int r = patch_rows_ > 0 ? patch_rows_ : (ph <= 256 ? 4 : 8);
+  // 8 rows per thread keep a 256-row patch in a cluster of 4 (one CTA per SM); 4 rows per thread for short patches
+  int r = patch_rows_ > 0 ? patch_rows_ : (ph > 128 ? 8 : 4);
   if (ceil_div(ph, 8 * r) > 8) r = 8;
   const int cl = (int)ceil_div(ph, 8 * r);
   if (cl > 8) return false;
@@ -1454,7 +1520,7 @@ void GridSolver::sweeps_async(int iters) {
   const PlaneGeom &g = geom_;
   if (stats_.unknowns == 0 || iters == 0) return;
   // batches of small patches and single small images: one persistent launch, the state never leaves the SMs
-  if ((batch_.batch > 0 || patch_single_) && iters >= patch_min_iters_ && patch_shape(nullptr, nullptr, nullptr)) {
+  if (iters >= patch_min_iters_ && patch_shape(nullptr, nullptr, nullptr)) {
     patch_sweeps(iters);
     return;
   }

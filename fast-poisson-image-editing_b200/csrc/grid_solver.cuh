@@ -24,7 +24,9 @@ constexpr int PAD_COLS = 32;  // >= round_up(MAX_BLOCK_K, 4), multiple of 32
 struct TileShape {
   int rows_per_thread;
   int warps;
-  int tile_h() const { return rows_per_thread * warps; }
+  int cluster = 1;  // CTAs of one thread-block cluster stacked vertically on one tile (grid_cluster.cuh)
+  int tile_h() const { return rows_per_thread * warps * cluster; }
+  int box_h() const { return rows_per_thread * warps; }  // rows one CTA stages per TMA box
 };
 
 // An EquSolver system whose unknowns are the masked pixels of an n x m crop in row-major order,
@@ -155,7 +157,7 @@ class GridSolver {
   cudaGraphExec_t graph_[2] = {nullptr, nullptr};
   bool graph_off_ = false, graph_warm_ = false;
   bool patch_off_ = false;      // persistent small-image kernel disabled
-  bool patch_single_ = true;    // ... also used for single (unbatched) small grids
+  bool patch_force_ = false;    // ... used even when too few items run side by side for it to pay
   int patch_rows_ = 0;          // rows per thread override (0 = automatic)
   int patch_min_iters_ = 32;    // shorter runs stay on the tiled kernel (the persistent launch reads and writes the planes once)
   int64_t patch_launches_ = 0;

@@ -148,9 +148,11 @@ int fpie_b200_grid_reset_from_images(fpie_b200_grid *g, const uint8_t *src, int 
 int fpie_b200_grid_reset_batch(fpie_b200_grid *g, const uint8_t *src, const uint8_t *mask, const uint8_t *tgt, int batch,
                                int rows, int cols, int mask_channels, int grad_mode);
 
-/* The persistent small-image kernel (csrc/patch.cuh): when the grid -- or every patch of a batch -- is at most
- * 512 rows x 256 columns and neither `variant` nor `block_k` was fixed at creation, a step of >= 32 sweeps is ONE
- * launch in which a thread-block cluster keeps a (patch, channel plane) in registers for all sweeps.
+/* The persistent small-image kernel (csrc/patch.cuh): when every patch of a batch is at most 512 rows x 256
+ * columns, the batch holds at least 4 patches (12 channel planes to run side by side; FPIE_B200_PATCH=2 lifts that
+ * limit, also for single images, FPIE_B200_PATCH=0 disables the kernel) and neither `variant` nor `block_k` was
+ * fixed at creation, a step of >= 32 sweeps is ONE launch in which a thread-block cluster keeps a (patch, channel
+ * plane) in registers for all sweeps.
  * *usable = 1 when the current problem qualifies; rows / cols per thread, CTAs per cluster; *launches = persistent
  * launches so far in the low 40 bits, clusters of the last launch above them. */
 int fpie_b200_grid_patch_info(fpie_b200_grid *g, int *usable, int *rows_per_thread, int *cols_per_thread, int *cluster,

@@ -111,11 +111,13 @@ def _full_batch(b, n, m, seed):
 def test_persistent_kernel_matches_oracle_and_mosaic(b, n, m, iters, full, monkeypatch):
     import fpie_b200
 
+    monkeypatch.setenv("FPIE_B200_PATCH", "2")  # (also for batches too small for the kernel to pay)
     src, mask, tgt = _full_batch(b, n, m, seed=n + m) if full else _batch(b, n, m, seed=n + m)
     proc = fpie_b200.BatchGridProcessor("max", "b200")
     proc.reset(src, mask, tgt)
     info = proc.core.patch_info()
     assert info["usable"] and info["cluster"] == -(-n // (8 * info["rows_per_thread"]))
+    assert info["rows_per_thread"] == (8 if n > 128 else 4)
     assert info["cols_per_thread"] == (4 if m <= 128 else 8)
     out, err = proc.step(iters)
     assert proc.core.patch_info()["launches"] == 1 and proc.core.info()["launches"] < 12
@@ -147,6 +149,7 @@ def test_persistent_kernel_single_images(kind, n, m, rows, monkeypatch):
     from fpie_b200 import synth
 
     monkeypatch.setenv("FPIE_B200_PATCH_ROWS", rows)
+    monkeypatch.setenv("FPIE_B200_PATCH", "2")  # a single image stays on the tiled kernel unless forced
     src, mask, tgt = synth.make_problem(kind, n, m, seed=7)
     proc = fpie_b200.GridProcessor("avg", "b200")
     proc.reset(src, mask, tgt, (0, 0), (0, 0))
@@ -177,3 +180,20 @@ def test_persistent_kernel_is_not_used_when_a_tile_shape_is_requested():
     core.reset_from_images(src, mask, tgt, (0, 0), (0, 0), "max")
     core.step(64)
     assert not core.patch_info()["usable"] and core.patch_info()["launches"] == 0
+
+
+def test_persistent_kernel_policy():
+    """Used by itself for batches of at least 4 small patches; one small image stays on the tiled kernel."""
+    import fpie_b200
+    from fpie_b200 import synth
+
+    src, mask, tgt = _full_batch(4, 64, 64, seed=2)
+    proc = fpie_b200.BatchGridProcessor("max", "b200")
+    proc.reset(src, mask, tgt)
+    assert proc.core.patch_info()["usable"]
+    proc.reset(src[:3], mask[:3], tgt[:3])
+    assert not proc.core.patch_info()["usable"]
+    one = fpie_b200.GridProcessor("max", "b200")
+    one.reset(*synth.make_problem("circle", 128, 128, seed=1), (0, 0), (0, 0))
+    one.step(64)
+    assert not one.core.patch_info()["usable"] and one.core.patch_info()["launches"] == 0

@@ -23,7 +23,7 @@ VARIANTS = [(100, 0), (39, 0), (39, 8), (24, 0), (24, 8), (24, 12), (36, 8), (36
             (18, 8), (25, 10), (0, 8), (0, 7), (0, 10), (11, 8), (105, 5), (0, 0), (0, 1), (0, 3), (0, 16), (1, 0),
             (2, 8), (3, 3), (4, 2), (5, 6), (6, 7), (7, 5), (8, 4), (9, 12), (10, 9), (12, 2), (20, 8), (20, 3),
             (21, 6), (22, 5), (120, 7), (40, 0), (40, 8), (40, 12), (40, 5), (41, 8), (41, 16), (41, 3), (42, 8),
-            (42, 6), (140, 7), (141, 12)]
+            (42, 6), (140, 7), (141, 12), (50, 0), (50, 8), (50, 12), (51, 8), (51, 16), (52, 5), (53, 8), (150, 8), (151, 7)]
 
 
 def _solver(variant=0, block_k=0):
@@ -107,7 +107,8 @@ def test_processor_matches_reference_golden(golden, name, mode):
 @pytest.mark.parametrize("variant,block_k", [(0, 0), (0, 5), (1, 0), (2, 16), (3, 3), (4, 8), (5, 12), (6, 4), (7, 16), (8, 8),
                                              (9, 3), (10, 10), (11, 1), (12, 7), (20, 0), (20, 13), (21, 4), (22, 16),
                                              (120, 8), (39, 8), (24, 8), (24, 3), (36, 16), (36, 5), (124, 8), (18, 12),
-                                             (40, 0), (40, 8), (40, 13), (41, 4), (41, 10), (42, 8), (42, 16), (140, 8)])
+                                             (40, 0), (40, 8), (40, 13), (41, 4), (41, 10), (42, 8), (42, 16), (140, 8),
+                                             (50, 8), (50, 3), (51, 8), (51, 13), (52, 10), (53, 6), (150, 8)])
 @pytest.mark.parametrize("shape,iters", [((3, 3), 4), ((4, 7), 9), ((61, 130), 37), ((257, 300), 50), ((300, 517), 23),
                                          ((700, 401), 40)])
 def test_random_grids_bitexact_vs_c_oracle(shape, iters, variant, block_k):
@@ -296,7 +297,7 @@ def test_full_size_temporal_blocking_invariance():
     ref = None
     # (272 sweeps: long enough for the default configuration to replay its CUDA graph of 16 passes)
     for variant, k in ((1, 0), (0, 0), (0, 8), (0, 16), (24, 12), (36, 8), (39, 8), (18, 8), (2, 4), (4, 8), (5, 12), (6, 5),
-                       (8, 8), (10, 6), (20, 8), (20, 12), (22, 6), (40, 8), (40, 12), (41, 8), (42, 10), (24, 8)):
+                       (8, 8), (10, 6), (20, 8), (20, 12), (22, 6), (40, 8), (40, 12), (41, 8), (42, 10), (24, 8), (50, 8), (51, 8), (51, 12), (52, 8), (53, 8)):
         proc = fpie_b200.GridProcessor("max", "b200")
         proc.core.close()
         try:
@@ -317,7 +318,7 @@ def test_full_size_temporal_blocking_invariance():
         proc.core.close()
 
 
-@pytest.mark.parametrize("variant,block_k,edge", [(0, 0, 40), (24, 8, 1), (36, 16, 100), (12, 4, 17), (20, 8, 30), (2, 8, 64), (40, 8, 30), (41, 12, 50)])
+@pytest.mark.parametrize("variant,block_k,edge", [(0, 0, 40), (24, 8, 1), (36, 16, 100), (12, 4, 17), (20, 8, 30), (2, 8, 64), (40, 8, 30), (41, 12, 50), (50, 8, 40), (51, 12, 64)])
 def test_split_passes_give_the_same_bits(variant, block_k, edge):
     """set_edge_rows / pass_async / flip (the row-band solver's overlap schedule): running a pass as
     edge tiles + interior tiles, in either order, is the same pass."""
@@ -380,7 +381,7 @@ def test_equ_formulation_on_the_grid_matches_the_equ_oracle():
         np.testing.assert_array_equal(s.state(), c_oracle.grid_sweeps(g.mask, g.t, g.g, 5))
 
 
-@pytest.mark.parametrize("variant,block_k", [(0, 0), (24, 3), (36, 2), (12, 1), (20, 2), (2, 2), (124, 4), (40, 3), (42, 2)])
+@pytest.mark.parametrize("variant,block_k", [(0, 0), (24, 3), (36, 2), (12, 1), (20, 2), (2, 2), (124, 4), (40, 3), (42, 2), (50, 3), (51, 2)])
 def test_long_runs_replay_a_cuda_graph(variant, block_k):
     """step(iters) with iters >= 32 passes replays a captured graph of 16 passes: same bits, from either
     state buffer, across resets (which drop the graph), and mixed with short steps."""
