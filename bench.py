@@ -357,7 +357,17 @@ def run_single(args, work, name):
     sweeps_per_launch = iters / sweep_launches
     achieved = per_update * unknowns * sweeps_per_launch / launch_s / 1e9
     peak, peak_src = measured_peak()
-    kernel = "grid_sweepk_pipe_kernel" if is_grid else "equ_sweep_kernel"
+    kernel = "grid_sweepk_pipe_kernel" if is_grid else (
+        "equ_sweep_lr_kernel" if core.info().get("path") == "gather-compact" else "equ_sweep_kernel")
+    patch = core.patch_info() if is_grid else None
+    if patch and patch["launches"] > 0:
+        # the persistent small-image kernel ran: ONE launch holds all sweeps of a step (csrc/patch.cuh)
+        kernel, sweep_launches, sweeps_per_launch = "grid_patch_kernel", 1, iters
+        launch_s = float(np.mean(sweep_ms)) * 1e-3
+        achieved = per_update * unknowns * sweeps_per_launch / launch_s / 1e9
+        kernel_cfg = {"kernel": "grid_patch_kernel", "rows_per_thread": patch["rows_per_thread"],
+                      "cols_per_thread": patch["cols_per_thread"], "ctas_per_cluster": patch["cluster"],
+                      "clusters": patch["clusters"], "warps": 8}
     roofline = {
         "bound": "hbm",
         "kernel": kernel,
@@ -366,7 +376,8 @@ def run_single(args, work, name):
         "unit": "GB/s",
         "frac": achieved / peak,
         # (the ncu capture is of config 2 for the grid kernel and of config 3 for the gather kernel)
-        "traffic": profiled_traffic(kernel) if (name == ("cfg2" if is_grid else "cfg3") and not args.size) else None,
+        "traffic": profiled_traffic("equ_sweep_kernel" if not is_grid else kernel)
+        if (name == ("cfg2" if is_grid else "cfg3") and not args.size) else None,
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": per_update * unknowns * sweeps_per_launch,
         "launch_us": launch_s * 1e6,

@@ -1687,6 +1687,7 @@ void GridSolver::run_pass(int nsweeps, const int2 *tiles, int ntiles) {
   a.xin = x_[cur_].ptr;
   a.xout = x_[cur_ ^ 1].ptr;
   a.tm_x = &tm_x_[cur_];
+  a.reverse = (serpentine_ && cur_) ? 1 : 0;  // (alternate passes walk their tile list backwards, as sweeps_async)
   launch_variant(variant_, a);
   stats_.launches += 1;
 }

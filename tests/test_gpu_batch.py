@@ -99,9 +99,9 @@ def _full_batch(b, n, m, seed):
 
 
 @pytest.mark.parametrize("b,n,m,iters,full", [
-    (5, 256, 256, 64, True),    # config 5 shape, full-square masks: the select-free (frame-only) stream, cluster of 8
+    (5, 256, 256, 64, True),    # config 5 shape, full-square masks: the select-free (frame-only) stream, cluster of 4
     (5, 256, 256, 45, False),   # ... arbitrary masks: per-pixel selects
-    (3, 64, 64, 100, True),     # 4 columns per thread, cluster of 2
+    (3, 64, 64, 100, True),     # 4 columns and 4 rows per thread, cluster of 2
     (4, 100, 128, 33, False),   # rows do not fill the cluster (padding rows), 4 columns per thread
     (3, 200, 252, 40, False),   # columns do not fill the warp
     (2, 300, 256, 37, True),    # 8 rows per thread (more than 256 rows)
