@@ -538,10 +538,21 @@ grid_residual_kernel(PlaneGeom g, BatchMap bm, int row_lo, int row_hi, const uin
     }
   }
   if (bm.batch > 0) {
-    // one residual triple per patch: groups never straddle patches (pw % 4 == 0), lanes of a warp may
-    if (acc != 0.f) {
+    // one residual triple per patch: groups never straddle patches (pw % 4 == 0), lanes of a warp may.  A warp
+    // that lies inside one patch (the common case) reduces by shuffles and issues ONE atomic -- per-thread
+    // atomics on three addresses per patch cost 8.9 ms per step on config 5 (profiles/r02_cfg5_launches.csv).
+    int id = -1;
+    if (q < per_plane) {
       const int r = row_lo + (int)(q / g.groups), grp = (int)(q % g.groups);
-      const int id = (r / bm.ph) * bm.bcols + (4 * grp) / bm.pw;
+      id = (r / bm.ph) * bm.bcols + (4 * grp) / bm.pw;
+    }
+    const int id0 = __shfl_sync(0xffffffffu, id, 0);
+    if (__all_sync(0xffffffffu, id == id0)) {
+      double v = (double)acc;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0 && id0 >= 0 && v != 0.0) atomicAdd(&err[(long long)id0 * 3 + p], v);
+    } else if (acc != 0.f) {
       atomicAdd(&err[(long long)id * 3 + p], (double)acc);
     }
     return;
