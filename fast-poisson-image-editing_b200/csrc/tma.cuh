@@ -102,14 +102,6 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
       : "memory");
 }
 
-// TMA prefetch of a 3-D box into L2 only (no shared memory, no barrier): takes the DRAM latency of a tile that
-// will be loaded one iteration later off that load's critical path
-__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(map)),
-               "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
