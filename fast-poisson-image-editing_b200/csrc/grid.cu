@@ -1327,8 +1327,6 @@ VariantInfo variant_info(int v) {
     case 51: return {21, 4, 2, true, 4};
     case 52: return {21, 4, 2, true, 3};
     case 53: return {14, 4, 3, true, 4};
-    case 43: return {14, 12, 1, true};
-    case 44: return {10, 16, 1, true};
 #ifdef FPIE_ALL_VARIANTS
     case 2: return {16, 8, 1, false};
     case 3: return {8, 16, 1, false};
@@ -1344,7 +1342,9 @@ VariantInfo variant_info(int v) {
     case 25: return {19, 8, 1, true};
     case 29: return {16, 4, 2, true};
     case 37: return {12, 4, 3, true};
+    case 43:  // (= 20 with this round's packed kernel)
     case 20: return {14, 12, 1, true};
+    case 44: return {10, 16, 1, true};
     case 21: return {16, 12, 1, true};
     case 22: return {12, 12, 1, true};
 #endif
@@ -1367,8 +1367,6 @@ static void launch_variant(int variant, const SweepArgs &a) {
     case 51: launch_cluster<21, 4, 2>(a, 4); break;
     case 52: launch_cluster<21, 4, 2>(a, 3); break;
     case 53: launch_cluster<14, 4, 3>(a, 4); break;
-    case 43: launch_pair<7, 12, 1>(a); break;
-    case 44: launch_pair<5, 16, 1>(a); break;
 #ifdef FPIE_ALL_VARIANTS
     case 2: launch_direct<16, 8>(a); break;
     case 3: launch_direct<8, 16>(a); break;
@@ -1384,7 +1382,9 @@ static void launch_variant(int variant, const SweepArgs &a) {
     case 25: launch_pipe<19, 8, 1>(a); break;
     case 29: launch_pipe<16, 4, 2>(a); break;
     case 37: launch_pipe<12, 4, 3>(a); break;
+    case 43:
     case 20: launch_pair<7, 12, 1>(a); break;
+    case 44: launch_pair<5, 16, 1>(a); break;
     case 21: launch_pair<8, 12, 1>(a); break;
     case 22: launch_pair<6, 12, 1>(a); break;
 #endif
