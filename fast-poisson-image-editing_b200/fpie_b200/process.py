@@ -79,7 +79,10 @@ class BaseProcessor:
                 break
         del old
         if canvas is None:
-            canvas = _lib.pinned_empty(tgt.shape, np.uint8)
+            try:
+                canvas = _lib.pinned_empty(tgt.shape, np.uint8)
+            except RuntimeError:  # page-locked memory exhausted: an ordinary array works, only slower
+                canvas = np.empty(tgt.shape, np.uint8)
             self._canvas_pool.append(canvas)
             del self._canvas_pool[:-3]  # (a dropped canvas lives on for as long as its holder keeps it)
         rows = tgt.shape[0]

@@ -92,5 +92,14 @@ def main() -> None:
     fpie_main()
 
 
+def gui_main() -> None:
+    """``fpie-gui`` with ``-b b200`` available (fpie/gui.py: reset + step per mouse click; a small edit is a
+    few hundred microseconds of reset and a step on the device)."""
+    register()
+    from fpie.gui import main as fpie_gui_main
+
+    fpie_gui_main()
+
+
 if __name__ == "__main__":
     main()
