@@ -340,7 +340,8 @@ template <int R, int NW, int OCC, bool H16>
 __global__ void __launch_bounds__(NW * 32, OCC)
 grid_sweepk_pipe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h,
                         const __grid_constant__ CUtensorMap tm_m, PlaneGeom g, float *__restrict__ xout,
-                        const int2 *__restrict__ tiles, int ntiles, int nsweeps, int halo_y, int halo_x, int reverse) {
+                        const int2 *__restrict__ tiles, int ntiles, int nsweeps, int halo_y, int halo_x, int reverse,
+                        unsigned int *__restrict__ edge_counter, int n_edge) {
   constexpr int TH = R * NW;
   using L = PipeSmem<R, NW, H16>;
   constexpr int H16_W = L::H16_W;
@@ -450,6 +451,14 @@ grid_sweepk_pipe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         const uint32_t on = ((rows_ok >> i) & 1u) && nib;
         st4_if(reinterpret_cast<char *>(out) + (size_t)i * pitch_bytes, x[i], on);
       }
+    }
+    // row bands: the first n_edge tiles of the list produce the rows the halo exchange sends; each bumps a device
+    // word once its rows are stored, and the halo stream waits on that word (cuStreamWaitValue32) -- the pass stays
+    // ONE launch and the exchange still starts as soon as the edge tiles are done (halo.cu)
+    if (t < n_edge) {
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) atomicAdd(edge_counter, 1u);
     }
     cur = nxt;
     nxt = nxt2;
@@ -737,7 +746,7 @@ GridSolver::GridSolver(int device, cudaStream_t stream, int block_k, int variant
   auto_k_ = (block_k <= 0);
   if (block_k <= 0) block_k = 8;
   FPIE_REQUIRE(block_k <= MAX_BLOCK_K, "block_k must be in 1..16");
-  configure(variant_ == 0 ? 39 : variant_, block_k);
+  configure(variant_ == 0 ? 24 : variant_, block_k);
   err_.resize(4);
   CUDA_CHECK(cudaMallocHost(&host_err_, 4 * sizeof(double)));
   const char *no_serp = getenv("FPIE_B200_NO_SERPENTINE");
@@ -748,6 +757,8 @@ GridSolver::GridSolver(int device, cudaStream_t stream, int block_k, int variant
   // FPIE_B200_PATCH_ROWS=4|8 overrides the rows per thread
   const char *patch = getenv("FPIE_B200_PATCH");
   patch_off_ = patch && patch[0] == '0';
+  const char *bsplit = getenv("FPIE_B200_BAND_SPLIT");
+  halo_split_last_ = bsplit && bsplit[0] == '1';
   patch_force_ = patch && patch[0] == '2';  // FPIE_B200_PATCH=2: also for fewer than 12 items (single images)
   const char *prow = getenv("FPIE_B200_PATCH_ROWS");
   patch_rows_ = prow ? atoi(prow) : 0;
@@ -1163,6 +1174,8 @@ struct SweepArgs {
   bool h16;
   int reverse;  // walk the tile list backwards (alternate passes: L2 reuse of the previous pass's last tiles)
   int ntiles, nsweeps, halo_y, halo_x;
+  unsigned int *edge_counter;  // band path: bumped by each of the first n_edge tiles (pipe kernels only)
+  int n_edge;
   bool load_only;  // resolve (load) the kernel and set its attributes, launch nothing
 };
 
@@ -1205,7 +1218,7 @@ void launch_pipe_h(const SweepArgs &a) {
   // (measured: a win once there is at least one tile per SM, a loss for grids of a few dozen tiles)
   cfg.numAttrs = (a.ntiles >= a.grid) ? 1 : 0;
   CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, *a.tm_x, *a.tm_h, *a.tm_m, a.g, a.xout, a.tiles, a.ntiles, a.nsweeps,
-                                a.halo_y, a.halo_x, a.reverse));
+                                a.halo_y, a.halo_x, a.reverse, a.edge_counter, a.n_edge));
 }
 
 template <int R, int NW, int OCC>
@@ -1305,29 +1318,35 @@ struct VariantInfo {
 
 // kernel variants (fpie_b200_grid_create `variant`): register-tile shape
 // rows/thread x warps, CTAs per SM; "pipe" = TMA-staged + split-phase exchange.
-// The default build carries the shapes the solver picks by itself plus the cross-check kernels;
-// -DFPIE_ALL_VARIANTS adds the measured-and-dominated shapes of DESIGN.md section 5 (test / tuning builds).
+// The default build carries the three shapes the solver picks by itself (12, 24, 36) plus two cross-check kernels
+// (1, 4); -DFPIE_ALL_VARIANTS adds every measured-and-dominated kernel of DESIGN.md section 5 -- round 1's tile
+// shapes, the packed-pair (FFMA2) kernels, the cluster kernels -- for test / tuning builds.
 VariantInfo variant_info(int v) {
   switch (v) {
     case 0:  // (automatic: replaced by a concrete shape at reset)
-    case 39: return {14, 12, 1, true};
-    case 1: return {16, 12, 1, false};  // (tile shape unused: one sweep per launch)
-    case 4: return {16, 12, 1, false};  // direct global -> register loads, no TMA staging
-    case 12: return {8, 8, 2, true};
     // two warps per scheduler: each sub-partition's 16384 registers then allow up to 255 per thread
     case 24: return {21, 8, 1, true};
+    case 1: return {16, 12, 1, false};  // (tile shape unused: one sweep per launch)
+    case 4: return {16, 12, 1, false};  // direct global -> register loads, no TMA staging (cross-check)
+    case 12: return {8, 8, 2, true};
     // four warps per CTA, several CTAs per SM: small tiles for small grids without giving up rows per thread
     case 36: return {21, 4, 2, true};
-    // packed-pair (FFMA2) kernels: rows = 2 x pair-rows per thread
+#ifdef FPIE_ALL_VARIANTS
+    case 39: return {14, 12, 1, true};  // round 1's first default
+    // packed-pair (FFMA2) kernels: rows = 2 x pair-rows per thread (grid_pair.cuh)
     case 40: return {22, 8, 1, true};
     case 41: return {20, 8, 1, true};
     case 42: return {20, 4, 2, true};
-    // cluster kernels: `cluster` CTAs of 4 warps x 21 rows stacked on one tile, two CTAs per SM
+    case 43:
+    case 20: return {14, 12, 1, true};
+    case 44: return {10, 16, 1, true};
+    case 21: return {16, 12, 1, true};
+    case 22: return {12, 12, 1, true};
+    // cluster kernels: `cluster` CTAs of 4 warps stacked on one tile (grid_cluster.cuh)
     case 50: return {21, 4, 2, true, 2};
     case 51: return {21, 4, 2, true, 4};
     case 52: return {21, 4, 2, true, 3};
     case 53: return {14, 4, 3, true, 4};
-#ifdef FPIE_ALL_VARIANTS
     case 2: return {16, 8, 1, false};
     case 3: return {8, 16, 1, false};
     case 5: return {16, 12, 1, true};
@@ -1342,32 +1361,32 @@ VariantInfo variant_info(int v) {
     case 25: return {19, 8, 1, true};
     case 29: return {16, 4, 2, true};
     case 37: return {12, 4, 3, true};
-    case 43:  // (= 20 with this round's packed kernel)
-    case 20: return {14, 12, 1, true};
-    case 44: return {10, 16, 1, true};
-    case 21: return {16, 12, 1, true};
-    case 22: return {12, 12, 1, true};
 #endif
-    default: throw Error("fpie_b200: unknown grid kernel variant (dominated shapes need a -DFPIE_ALL_VARIANTS build)");
+    default: throw Error("fpie_b200: unknown grid kernel variant (measured-and-dominated shapes need a -DFPIE_ALL_VARIANTS build)");
   }
 }
 
 // one pass of the tiled kernel in the register-tile shape `variant` names
 static void launch_variant(int variant, const SweepArgs &a) {
   switch (variant) {
-    case 39: launch_pipe<14, 12, 1>(a); break;
+    case 24: launch_pipe<21, 8, 1>(a); break;
     case 4: launch_direct<16, 12>(a); break;
     case 12: launch_pipe<8, 8, 2>(a); break;
-    case 24: launch_pipe<21, 8, 1>(a); break;
     case 36: launch_pipe<21, 4, 2>(a); break;
+#ifdef FPIE_ALL_VARIANTS
+    case 39: launch_pipe<14, 12, 1>(a); break;
     case 40: launch_pair<11, 8, 1>(a); break;
     case 41: launch_pair<10, 8, 1>(a); break;
     case 42: launch_pair<10, 4, 2>(a); break;
+    case 43:
+    case 20: launch_pair<7, 12, 1>(a); break;
+    case 44: launch_pair<5, 16, 1>(a); break;
+    case 21: launch_pair<8, 12, 1>(a); break;
+    case 22: launch_pair<6, 12, 1>(a); break;
     case 50: launch_cluster<21, 4, 2>(a, 2); break;
     case 51: launch_cluster<21, 4, 2>(a, 4); break;
     case 52: launch_cluster<21, 4, 2>(a, 3); break;
     case 53: launch_cluster<14, 4, 3>(a, 4); break;
-#ifdef FPIE_ALL_VARIANTS
     case 2: launch_direct<16, 8>(a); break;
     case 3: launch_direct<8, 16>(a); break;
     case 5: launch_pipe<16, 12, 1>(a); break;
@@ -1382,13 +1401,8 @@ static void launch_variant(int variant, const SweepArgs &a) {
     case 25: launch_pipe<19, 8, 1>(a); break;
     case 29: launch_pipe<16, 4, 2>(a); break;
     case 37: launch_pipe<12, 4, 3>(a); break;
-    case 43:
-    case 20: launch_pair<7, 12, 1>(a); break;
-    case 44: launch_pair<5, 16, 1>(a); break;
-    case 21: launch_pair<8, 12, 1>(a); break;
-    case 22: launch_pair<6, 12, 1>(a); break;
 #endif
-    default: throw Error("fpie_b200: unknown grid kernel variant (dominated shapes need a -DFPIE_ALL_VARIANTS build)");
+    default: throw Error("fpie_b200: unknown grid kernel variant (measured-and-dominated shapes need a -DFPIE_ALL_VARIANTS build)");
   }
 }
 
@@ -1643,9 +1657,20 @@ void GridSolver::set_edge_rows(int rows) {
       CUDA_CHECK(cudaMemcpyAsync(tiles_part_[p].ptr, part[p].data(), part[p].size() * sizeof(int2),
                                  cudaMemcpyHostToDevice, stream_));
   }
+  // edge tiles first, then the interior: the one-launch form of a pass whose edge rows are sent (halo.cu)
+  std::vector<int2> all = part[0];
+  all.insert(all.end(), part[1].begin(), part[1].end());
+  tiles_edge_first_.resize(std::max<size_t>(all.size(), 1));
+  if (!all.empty())
+    CUDA_CHECK(cudaMemcpyAsync(tiles_edge_first_.ptr, all.data(), all.size() * sizeof(int2), cudaMemcpyHostToDevice,
+                               stream_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));  // (the host vectors go out of scope)
   edge_rows_ = rows;
 }
+
+bool GridSolver::variant_counts_edges() const { return variant_info(variant_).pipe && variant_info(variant_).cluster == 1 &&
+                                                       variant_ != 40 && variant_ != 41 && variant_ != 42 && variant_ != 43 &&
+                                                       variant_ != 44 && variant_ != 20 && variant_ != 21 && variant_ != 22; }
 
 void GridSolver::pass_async(int nsweeps, int part) {
   require_ready();
@@ -1679,7 +1704,7 @@ void GridSolver::preload_kernels() {
 }
 
 // one pass (<= block_k sweeps) over the tiles of `tiles`, current buffer -> other buffer, no flip
-void GridSolver::run_pass(int nsweeps, const int2 *tiles, int ntiles) {
+void GridSolver::run_pass(int nsweeps, const int2 *tiles, int ntiles, unsigned int *edge_counter, int n_edge) {
   if (stats_.unknowns == 0 || ntiles == 0) return;
   SweepArgs a{};
   a.grid = sm_count_;
@@ -1698,7 +1723,9 @@ void GridSolver::run_pass(int nsweeps, const int2 *tiles, int ntiles) {
   a.xin = x_[cur_].ptr;
   a.xout = x_[cur_ ^ 1].ptr;
   a.tm_x = &tm_x_[cur_];
-  a.reverse = (serpentine_ && cur_) ? 1 : 0;  // (alternate passes walk their tile list backwards, as sweeps_async)
+  a.reverse = (serpentine_ && cur_ && n_edge == 0) ? 1 : 0;  // (alternate passes walk their tile list backwards)
+  a.edge_counter = edge_counter;
+  a.n_edge = n_edge;
   launch_variant(variant_, a);
   stats_.launches += 1;
 }
