@@ -340,8 +340,7 @@ template <int R, int NW, int OCC, bool H16>
 __global__ void __launch_bounds__(NW * 32, OCC)
 grid_sweepk_pipe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_h,
                         const __grid_constant__ CUtensorMap tm_m, PlaneGeom g, float *__restrict__ xout,
-                        const int2 *__restrict__ tiles, int ntiles, int nsweeps, int halo_y, int halo_x, int reverse,
-                        unsigned int *__restrict__ edge_counter, int n_edge) {
+                        const int2 *__restrict__ tiles, int ntiles, int nsweeps, int halo_y, int halo_x, int reverse) {
   constexpr int TH = R * NW;
   using L = PipeSmem<R, NW, H16>;
   constexpr int H16_W = L::H16_W;
@@ -451,14 +450,6 @@ grid_sweepk_pipe_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         const uint32_t on = ((rows_ok >> i) & 1u) && nib;
         st4_if(reinterpret_cast<char *>(out) + (size_t)i * pitch_bytes, x[i], on);
       }
-    }
-    // row bands: the first n_edge tiles of the list produce the rows the halo exchange sends; each bumps a device
-    // word once its rows are stored, and the halo stream waits on that word (cuStreamWaitValue32) -- the pass stays
-    // ONE launch and the exchange still starts as soon as the edge tiles are done (halo.cu)
-    if (t < n_edge) {
-      __threadfence();
-      __syncthreads();
-      if (threadIdx.x == 0) atomicAdd(edge_counter, 1u);
     }
     cur = nxt;
     nxt = nxt2;
@@ -757,8 +748,6 @@ GridSolver::GridSolver(int device, cudaStream_t stream, int block_k, int variant
   // FPIE_B200_PATCH_ROWS=4|8 overrides the rows per thread
   const char *patch = getenv("FPIE_B200_PATCH");
   patch_off_ = patch && patch[0] == '0';
-  const char *bsplit = getenv("FPIE_B200_BAND_SPLIT");
-  halo_split_last_ = bsplit && bsplit[0] == '1';
   patch_force_ = patch && patch[0] == '2';  // FPIE_B200_PATCH=2: also for fewer than 12 items (single images)
   const char *prow = getenv("FPIE_B200_PATCH_ROWS");
   patch_rows_ = prow ? atoi(prow) : 0;
@@ -1174,8 +1163,6 @@ struct SweepArgs {
   bool h16;
   int reverse;  // walk the tile list backwards (alternate passes: L2 reuse of the previous pass's last tiles)
   int ntiles, nsweeps, halo_y, halo_x;
-  unsigned int *edge_counter;  // band path: bumped by each of the first n_edge tiles (pipe kernels only)
-  int n_edge;
   bool load_only;  // resolve (load) the kernel and set its attributes, launch nothing
 };
 
@@ -1218,7 +1205,7 @@ void launch_pipe_h(const SweepArgs &a) {
   // (measured: a win once there is at least one tile per SM, a loss for grids of a few dozen tiles)
   cfg.numAttrs = (a.ntiles >= a.grid) ? 1 : 0;
   CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, *a.tm_x, *a.tm_h, *a.tm_m, a.g, a.xout, a.tiles, a.ntiles, a.nsweeps,
-                                a.halo_y, a.halo_x, a.reverse, a.edge_counter, a.n_edge));
+                                a.halo_y, a.halo_x, a.reverse));
 }
 
 template <int R, int NW, int OCC>
@@ -1657,20 +1644,10 @@ void GridSolver::set_edge_rows(int rows) {
       CUDA_CHECK(cudaMemcpyAsync(tiles_part_[p].ptr, part[p].data(), part[p].size() * sizeof(int2),
                                  cudaMemcpyHostToDevice, stream_));
   }
-  // edge tiles first, then the interior: the one-launch form of a pass whose edge rows are sent (halo.cu)
-  std::vector<int2> all = part[0];
-  all.insert(all.end(), part[1].begin(), part[1].end());
-  tiles_edge_first_.resize(std::max<size_t>(all.size(), 1));
-  if (!all.empty())
-    CUDA_CHECK(cudaMemcpyAsync(tiles_edge_first_.ptr, all.data(), all.size() * sizeof(int2), cudaMemcpyHostToDevice,
-                               stream_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));  // (the host vectors go out of scope)
   edge_rows_ = rows;
 }
 
-bool GridSolver::variant_counts_edges() const { return variant_info(variant_).pipe && variant_info(variant_).cluster == 1 &&
-                                                       variant_ != 40 && variant_ != 41 && variant_ != 42 && variant_ != 43 &&
-                                                       variant_ != 44 && variant_ != 20 && variant_ != 21 && variant_ != 22; }
 
 void GridSolver::pass_async(int nsweeps, int part) {
   require_ready();
@@ -1704,7 +1681,7 @@ void GridSolver::preload_kernels() {
 }
 
 // one pass (<= block_k sweeps) over the tiles of `tiles`, current buffer -> other buffer, no flip
-void GridSolver::run_pass(int nsweeps, const int2 *tiles, int ntiles, unsigned int *edge_counter, int n_edge) {
+void GridSolver::run_pass(int nsweeps, const int2 *tiles, int ntiles) {
   if (stats_.unknowns == 0 || ntiles == 0) return;
   SweepArgs a{};
   a.grid = sm_count_;
@@ -1723,9 +1700,7 @@ void GridSolver::run_pass(int nsweeps, const int2 *tiles, int ntiles, unsigned i
   a.xin = x_[cur_].ptr;
   a.xout = x_[cur_ ^ 1].ptr;
   a.tm_x = &tm_x_[cur_];
-  a.reverse = (serpentine_ && cur_ && n_edge == 0) ? 1 : 0;  // (alternate passes walk their tile list backwards)
-  a.edge_counter = edge_counter;
-  a.n_edge = n_edge;
+  a.reverse = (serpentine_ && cur_) ? 1 : 0;  // (alternate passes walk their tile list backwards, as sweeps_async)
   launch_variant(variant_, a);
   stats_.launches += 1;
 }

@@ -167,7 +167,6 @@ class GridSolver {
   std::vector<int2> host_tiles_;
   std::vector<int> host_tile_row_;
   DeviceBuffer<int2> tiles_part_[2];
-  DeviceBuffer<int2> tiles_edge_first_;  // edge tiles, then interior tiles
   int n_part_[2] = {0, 0};
   int edge_rows_ = 0;
   CUtensorMap tm_x_[2];
@@ -188,22 +187,19 @@ class GridSolver {
     uint32_t sent = 0, received = 0;    // exchange intervals so far (the flag words carry these counters)
   };
   void halo_free_side(HaloSide &s);
-  void halo_send(int which, bool counted = false);
+  void halo_send(int which);
   void halo_recv(int which);
-  void run_pass(int nsweeps, const int2 *tiles, int ntiles, unsigned int *edge_counter = nullptr, int n_edge = 0);
-  bool variant_counts_edges() const;  // the kernel in use bumps the edge counter (TMA-pipelined scalar kernels)
+  void run_pass(int nsweeps, const int2 *tiles, int ntiles);
   void preload_kernels();
   bool patch_shape(int *rows_per_thread, int *cols_per_thread, int *cluster) const;
   void patch_sweeps(int iters);
   HaloSide halo_[2];
   int band_lo_ = 0, band_hi_ = 0;
   bool halo_pending_ = false;
-  bool halo_split_last_ = false;  // FPIE_B200_BAND_SPLIT=1: keep the last pass of an interval as two launches
   int64_t halo_exchanges_ = 0;
   cudaStream_t halo_stream_ = nullptr;
   cudaEvent_t ev_edge_ = nullptr, ev_sent_ = nullptr;
-  uint32_t *halo_seq_ = nullptr;  // device: [2] flag values in flight (source of the 4-byte flag copies), [2] = edge tiles done
-  uint32_t edge_target_ = 0;      // value of the edge counter once the edge tiles of every counted pass so far are done
+  uint32_t *halo_seq_ = nullptr;  // device: [2] flag values in flight (source of the 4-byte flag copies)
   // trace
   std::vector<cudaEvent_t> trace_ev_;
   std::vector<int> trace_tag_;

@@ -125,9 +125,8 @@ bool GridSolver::halo_config(int band_lo, int band_hi, bool force) {
   CUDA_CHECK(cudaStreamCreateWithFlags(&halo_stream_, cudaStreamNonBlocking));
   CUDA_CHECK(cudaEventCreateWithFlags(&ev_edge_, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventCreateWithFlags(&ev_sent_, cudaEventDisableTiming));
-  CUDA_CHECK(cudaMalloc(&halo_seq_, 3 * sizeof(uint32_t)));
-  CUDA_CHECK(cudaMemset(halo_seq_, 0, 3 * sizeof(uint32_t)));
-  edge_target_ = 0;
+  CUDA_CHECK(cudaMalloc(&halo_seq_, 2 * sizeof(uint32_t)));
+  CUDA_CHECK(cudaMemset(halo_seq_, 0, 2 * sizeof(uint32_t)));
   for (int side = 0; side < 2; ++side) {
     HaloSide &s = halo_[side];
     s.rows = rows[side];
@@ -253,15 +252,10 @@ int GridSolver::halo_trace_read(float *out, int max_floats) {
 
 // Band-edge rows of state buffer `which` -> the neighbours' inboxes, on the halo stream, ordered after
 // everything the solver's stream holds so far (the edge tiles that produced those rows).
-void GridSolver::halo_send(int which, bool counted) {
+void GridSolver::halo_send(int which) {
   const PlaneGeom &g = geom_;
-  if (counted) {
-    // the pass is one launch: its edge tiles (first in the list) bump a device word as they finish
-    stream_wait_geq(halo_stream_, halo_seq_ + 2, edge_target_);
-  } else {
-    CUDA_CHECK(cudaEventRecord(ev_edge_, stream_));
-    CUDA_CHECK(cudaStreamWaitEvent(halo_stream_, ev_edge_, 0));
-  }
+  CUDA_CHECK(cudaEventRecord(ev_edge_, stream_));
+  CUDA_CHECK(cudaStreamWaitEvent(halo_stream_, ev_edge_, 0));
   trace_mark(10, halo_stream_);
   const size_t row_bytes = (size_t)g.m * sizeof(float), pitch_bytes = (size_t)g.pitch * sizeof(float);
   for (int side = 0; side < 2; ++side) {
@@ -330,8 +324,6 @@ void GridSolver::band_sweeps_async(int iters) {
   int left = iters;
   const int k = block_k_;
   int interval = 0;
-  // (the last pass of an interval as one launch needs a kernel that counts its edge tiles, and some edge tiles)
-  const bool one_launch = !halo_split_last_ && variant_counts_edges() && n_part_[0] > 0 && stats_.unknowns > 0;
   while (left > 0) {
     const int s = std::min(depth, left);
     const int npass = (int)ceil_div(s, k);
@@ -353,12 +345,6 @@ void GridSolver::band_sweeps_async(int iters) {
         halo_recv(cur_);
         run_pass(ns, tiles_part_[0].ptr, n_part_[0]);
         trace_mark(6, stream_);
-      } else if (last && one_launch) {
-        // ONE launch, edge tiles first; the halo stream starts the exchange when the in-kernel counter says so
-        edge_target_ += (uint32_t)n_part_[0];
-        run_pass(ns, tiles_edge_first_.ptr, n_part_[0] + n_part_[1], halo_seq_ + 2, n_part_[0]);
-        halo_send(cur_ ^ 1, true);
-        trace_mark(3, stream_);
       } else if (last) {
         run_pass(ns, tiles_part_[0].ptr, n_part_[0]);
         trace_mark(2, stream_);
