@@ -49,6 +49,14 @@ WORKLOADS = {
 }
 
 
+def equ_kernel_name(info):
+    """The gather kernel EquSolver.sweeps_async launches for this system (csrc/equ.cu): 4-byte distance table (+ fp16
+    B stream) for row-major systems beyond the L2, 8-byte (up, down) table for smaller ones, int4 table otherwise."""
+    if info.get("path") != "gather-compact":
+        return "equ_sweep_kernel"
+    return "equ_sweep_d16_kernel" if (info.get("table") or "").startswith("delta16") else "equ_sweep_lr_kernel"
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -357,8 +365,7 @@ def run_single(args, work, name):
     sweeps_per_launch = iters / sweep_launches
     achieved = per_update * unknowns * sweeps_per_launch / launch_s / 1e9
     peak, peak_src = measured_peak()
-    kernel = "grid_sweepk_pipe_kernel" if is_grid else (
-        "equ_sweep_lr_kernel" if core.info().get("path") == "gather-compact" else "equ_sweep_kernel")
+    kernel = "grid_sweepk_pipe_kernel" if is_grid else equ_kernel_name(core.info())
     patch = core.patch_info() if is_grid else None
     if patch and patch["launches"] > 0:
         # the persistent small-image kernel ran: ONE launch holds all sweeps of a step (csrc/patch.cuh)
@@ -376,7 +383,7 @@ def run_single(args, work, name):
         "unit": "GB/s",
         "frac": achieved / peak,
         # (the ncu capture is of config 2 for the grid kernel and of config 3 for the gather kernel)
-        "traffic": profiled_traffic("equ_sweep_kernel" if not is_grid else kernel)
+        "traffic": profiled_traffic(kernel)
         if (name == ("cfg2" if is_grid else "cfg3") and not args.size) else None,
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": per_update * unknowns * sweeps_per_launch,
@@ -467,6 +474,7 @@ def run_single(args, work, name):
                    "working set fits the 126 MB L2 (L2-resident configuration; reported separately from the HBM runs)"),
             "reset_s": reset_s,
             "solver_path": core.info().get("path") if not is_grid else "tiled",
+            "equ_table": core.info().get("table") if not is_grid else None,
         },
         "roofline": roofline,
         "cpu_baseline": base,

@@ -13,6 +13,8 @@
 #include <cstring>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 
 #include "equ_solver.cuh"
@@ -133,14 +135,32 @@ __global__ void check_index_kernel(long long N, const int4 *__restrict__ A, int 
 // Compact neighbour table for row-major ids: when left / right are always "absent" or i-1 / i+1
 // (true for every system built from a row-major partition) only up / down need to be stored;
 // bit 31 of each carries "left present" / "right present".  16 -> 8 bytes per unknown per sweep.
+// A second, 4-byte form holds the up / down neighbours as 15-bit DISTANCES (up = i - du, down = i + dd,
+// 0 = absent; bits 15 / 31 = left / right present): row-major ids put them less than one image row of unknowns
+// away.  flags bit 0: not structured; bit 1: some distance does not fit (the 8-byte table is used then).
 __global__ void compact_index_kernel(long long N, const int4 *__restrict__ A, int2 *__restrict__ UD,
-                                     int *__restrict__ unstructured) {
+                                     uint32_t *__restrict__ D16, int *__restrict__ flags) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= N) return;
   const int4 a = A[i];
   const bool ok = (a.z == 0 || a.z == i - 1) && (a.w == 0 || a.w == i + 1);
-  if (!ok) atomicExch(unstructured, 1);
+  if (!ok) atomicOr(flags, 1);
   UD[i] = make_int2(a.x | (a.z != 0 ? (int)0x80000000 : 0), a.y | (a.w != 0 ? (int)0x80000000 : 0));
+  const long long du = a.x ? i - a.x : 0, dd = a.y ? a.y - i : 0;
+  if ((a.x && (du <= 0 || du > 0x7fff)) || (a.y && (dd <= 0 || dd > 0x7fff))) atomicOr(flags, 2);
+  D16[i] = (uint32_t)(du & 0x7fff) | (a.z != 0 ? 0x8000u : 0u) | ((uint32_t)(dd & 0x7fff) << 16) | (a.w != 0 ? 0x80000000u : 0u);
+}
+
+// fp16 copy of B for the compact gather kernel; *inexact is raised when a value does not survive the round trip
+// (B = gradient + boundary targets of uint8 images: halves below 1024 always do)
+__global__ void equ_b_to_half_kernel(long long N, long long pitch, const float *__restrict__ src,
+                                     __half *__restrict__ dst, int *__restrict__ inexact) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= pitch * 3 || (i % pitch) >= N) return;  // (the padding behind row N - 1 is never read)
+  const float v = src[i];
+  const __half h = __float2half_rn(v);
+  dst[i] = h;
+  if (!(__half2float(h) == v)) atomicOr(inexact, 4);
 }
 
 // Does A describe exactly the 4-neighbour structure of the mask that partition() labelled?
@@ -194,6 +214,69 @@ equ_sweep_lr_kernel(long long N, long long pitch, const int2 *__restrict__ UD, c
     s = __fadd_rn(s, x[lf]);
     s = __fadd_rn(s, x[rt]);
     xout[ch * pitch + i] = __fmul_rn(s, 0.25f);
+  }
+}
+
+// The same update from the 4-byte distance table and (BH) the fp16 copy of B: 4 + 6 + 12 + 12 = 34 bytes per
+// unknown and sweep instead of the 52 of the reference layout (A 16 + B 12 + X 12 + X' 12) -- same operands, same
+// add order, same bits.  A thread owns FOUR consecutive unknowns: table, B and the centre values arrive as one
+// 128-bit (64-bit) load each, left / right neighbours of the inner three come from registers, and only the up /
+// down gathers stay scalar -- 9 instead of 17 memory requests per unknown (the scalar form of this kernel was
+// request-bound: 4.6 TB/s of DRAM traffic against 5.4 TB/s for the 8-byte table).
+template <bool BH>
+__global__ void __launch_bounds__(256)
+equ_sweep_d16_kernel(long long N, long long pitch, const uint32_t *__restrict__ D16, const float *__restrict__ B,
+                     const __half *__restrict__ B16, const float *__restrict__ xin, float *__restrict__ xout) {
+  const long long i0 = 4 * (blockIdx.x * (long long)blockDim.x + threadIdx.x);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // (see equ_sweep_lr_kernel)
+  if (i0 >= N) return;
+  const uint4 tv = *reinterpret_cast<const uint4 *>(D16 + i0);  // (the table is zero-padded to the pitch)
+  const uint32_t t[4] = {tv.x, tv.y, tv.z, tv.w};
+  float b[3][4];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    if (BH) {
+      const uint2 raw = *reinterpret_cast<const uint2 *>(B16 + ch * pitch + i0);
+      const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&raw.x));
+      const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&raw.y));
+      b[ch][0] = lo.x, b[ch][1] = lo.y, b[ch][2] = hi.x, b[ch][3] = hi.y;
+    } else {
+      const float4 v = ld4(B + ch * pitch + i0);
+      b[ch][0] = v.x, b[ch][1] = v.y, b[ch][2] = v.z, b[ch][3] = v.w;
+    }
+  }
+  long long up[4], dn[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t du = t[j] & 0x7fffu, dd = (t[j] >> 16) & 0x7fffu;
+    up[j] = du ? i0 + j - du : 0;
+    dn[j] = dd ? i0 + j + dd : 0;
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const float *x = xin + ch * pitch;
+    const float4 cv = ld4(x + i0);
+    const float c[4] = {cv.x, cv.y, cv.z, cv.w};
+    const float zero_row = x[0];  // what an absent neighbour reads (row 0, the constant)
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float lf = (t[j] & 0x8000u) ? (j > 0 ? c[j > 0 ? j - 1 : 0] : x[i0 - 1]) : zero_row;
+      const float rt = (t[j] >> 31) ? (j < 3 ? c[j < 3 ? j + 1 : 3] : x[i0 + 4]) : zero_row;
+      float s = __fadd_rn(b[ch][j], x[up[j]]);
+      s = __fadd_rn(s, x[dn[j]]);
+      s = __fadd_rn(s, lf);
+      s = __fadd_rn(s, rt);
+      o[j] = __fmul_rn(s, 0.25f);
+    }
+    if (i0 + 3 < N) {
+      st4(xout + ch * pitch + i0, make_float4(o[0], o[1], o[2], o[3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (i0 + j < N) xout[ch * pitch + i0 + j] = o[j];
+    }
   }
 }
 
@@ -380,6 +463,12 @@ static int blocks_for(long long work, int threads) { return (int)ceil_div(work, 
 EquSolver::EquSolver(int device, cudaStream_t stream, int block_size) : device_(device), stream_(stream) {
   const char *no_graph = getenv("FPIE_B200_NO_GRAPH");
   graph_off_ = no_graph && no_graph[0] && no_graph[0] != '0';
+  const char *no_d16 = getenv("FPIE_B200_NO_DELTA16");  // A/B: keep the 8-byte (up, down) table and fp32 B
+  no_delta16_ = no_d16 && no_d16[0] && no_d16[0] != '0';
+  // The 4-byte table pays off when the sweep streams from HBM (config 3: +10 %); an L2-resident system is faster
+  // with one unknown per thread (config 1: 5.6 vs 7.1 us per sweep), so small systems keep the 8-byte table.
+  const char *d16_min = getenv("FPIE_B200_DELTA16_MIN");
+  delta16_min_ = d16_min && d16_min[0] ? atoll(d16_min) : (1ll << 21);
   int count = 0;
   CUDA_CHECK(cudaGetDeviceCount(&count));
   FPIE_REQUIRE(device >= 0 && device < count, "fpie_b200: no such CUDA device");
@@ -561,13 +650,19 @@ void EquSolver::compact_tables() {
   structured_ = false;
   if (mode_ != 0) return;
   ud_.resize((size_t)N_);
+  d16_.resize((size_t)pitch_);
+  CUDA_CHECK(cudaMemsetAsync(d16_.ptr, 0, d16_.bytes(), stream_));
+  b16_.resize((size_t)pitch_ * 3);
   CUDA_CHECK(cudaMemsetAsync(flag_.ptr, 0, sizeof(int), stream_));
-  compact_index_kernel<<<blocks_for(N_, 256), 256, 0, stream_>>>(N_, A_.ptr, ud_.ptr, flag_.ptr);
+  compact_index_kernel<<<blocks_for(N_, 256), 256, 0, stream_>>>(N_, A_.ptr, ud_.ptr, d16_.ptr, flag_.ptr);
+  equ_b_to_half_kernel<<<blocks_for(pitch_ * 3, 256), 256, 0, stream_>>>(N_, pitch_, B_.ptr, b16_.ptr, flag_.ptr);
   CUDA_CHECK(cudaGetLastError());
-  stats_.launches += 1;
+  stats_.launches += 2;
   CUDA_CHECK(cudaMemcpyAsync(host_flag_, flag_.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream_));
   CUDA_CHECK(cudaStreamSynchronize(stream_));
-  structured_ = (*host_flag_ == 0) && !force_generic_;
+  structured_ = ((*host_flag_ & 1) == 0) && !force_generic_;
+  delta16_ = structured_ && ((*host_flag_ & 2) == 0) && !no_delta16_ && N_ >= delta16_min_;
+  b16_ok_ = delta16_ && ((*host_flag_ & 4) == 0);
 }
 
 void EquSolver::reset_from_images(const uint8_t *src, int sh, int sw, const uint8_t *mask, int mh, int mw, int mc,
@@ -670,7 +765,16 @@ void EquSolver::sweeps_async(int iters) {
     const float *xin = X_[cur].ptr;
     float *xout = X_[cur ^ 1].ptr;
     const float *b = B_.ptr;
-    if (structured_) {
+    if (delta16_) {
+      const uint32_t *d16 = d16_.ptr;
+      const __half *b16 = b16_.ptr;
+      cfg.blockDim = dim3(256);
+      cfg.gridDim = dim3((unsigned)blocks_for((N_ + 3) / 4, 256));
+      if (b16_ok_)
+        CUDA_CHECK(cudaLaunchKernelEx(&cfg, equ_sweep_d16_kernel<true>, (long long)N_, (long long)pitch_, d16, b, b16, xin, xout));
+      else
+        CUDA_CHECK(cudaLaunchKernelEx(&cfg, equ_sweep_d16_kernel<false>, (long long)N_, (long long)pitch_, d16, b, b16, xin, xout));
+    } else if (structured_) {
       const int2 *ud = ud_.ptr;
       CUDA_CHECK(cudaLaunchKernelEx(&cfg, equ_sweep_lr_kernel, (long long)N_, (long long)pitch_, ud, b, xin, xout));
     } else {

@@ -1,6 +1,8 @@
 // EquSolver: index-mapped (gather) Jacobi on a compacted list of unknowns.
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include <memory>
 
 #include "common.cuh"
@@ -37,8 +39,14 @@ class EquSolver {
   const EquStats &stats() const { return stats_; }
   int64_t launches() const { return stats_.launches + (tiled_ ? tiled_->stats().launches : 0); }
   bool structured() const { return structured_; }
-  // 0 = generic int4 gather, 1 = compact-table gather, 2 = promoted to the tiled grid kernel, 3 = red-black
-  int path() const { return mode_ == 1 ? 3 : (promoted_ ? 2 : (structured_ ? 1 : 0)); }
+  // 0 = generic int4 gather, 1 = compact-table gather (bit 3 set: 4-byte distance table; bit 4: fp16 B stream),
+  // 2 = promoted to the tiled grid kernel, 3 = red-black
+  int path() const {
+    if (mode_ == 1) return 3;
+    if (promoted_) return 2;
+    if (!structured_) return 0;
+    return 1 | (delta16_ ? 8 : 0) | (b16_ok_ ? 16 : 0);
+  }
 
  private:
   void require_ready() const;
@@ -63,6 +71,10 @@ class EquSolver {
   int cur_ = 0;
   DeviceBuffer<int4> A_;
   DeviceBuffer<int2> ud_;      // compact table (up, down, left/right presence bits)
+  DeviceBuffer<uint32_t> d16_; // 4-byte table: 15-bit distances to up / down + presence bits
+  DeviceBuffer<__half> b16_;   // fp16 copy of B (streamed when every value is exactly representable)
+  bool delta16_ = false, b16_ok_ = false, no_delta16_ = false;
+  long long delta16_min_ = 1ll << 21;  // unknowns from which the 4-byte table is used (working set beyond the L2)
   bool structured_ = false;    // left/right are always i-1 / i+1 or absent
   bool force_generic_ = false;
   // promotion to the temporally blocked grid kernel (row-major ids on a known crop)

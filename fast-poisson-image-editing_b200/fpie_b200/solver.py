@@ -544,7 +544,10 @@ class EquSolver(_Handle):
         unk, launches, path = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int()
         _lib.check(self._lib.fpie_b200_equ_info(self.handle, ctypes.byref(unk), ctypes.byref(launches),
                                                 ctypes.byref(path)))
-        return dict(unknowns=unk.value, launches=launches.value, path=self.PATHS[path.value])
+        code = path.value
+        # gather-compact with its table / B-stream form in `table`: the path NAME stays what callers test for
+        table = {1: "int2 + fp32 B", 9: "delta16 + fp32 B", 25: "delta16 + fp16 B"}.get(code)
+        return dict(unknowns=unk.value, launches=launches.value, path=self.PATHS[code & 7], table=table)
 
     def _need_reset(self):
         if self.N <= 0:

@@ -286,7 +286,8 @@ int fpie_b200_equ_sweeps_async(fpie_b200_equ *e, int iters);
 int fpie_b200_equ_finish_async(fpie_b200_equ *e);
 int fpie_b200_equ_sync(fpie_b200_equ *e);
 int fpie_b200_equ_fetch(fpie_b200_equ *e, uint8_t *out_img, float *out_err3);
-/* path: 0 = generic int4 gather, 1 = compact-table gather, 2 = promoted to the tiled grid kernel, 3 = red-black */
+/* path & 7: 0 = generic int4 gather, 1 = compact-table gather (bit 3: the 4-byte distance table, bit 4: fp16 B stream --
+ * 34 instead of 52 bytes per unknown and sweep, same bits), 2 = promoted to the tiled grid kernel, 3 = red-black */
 int fpie_b200_equ_info(fpie_b200_equ *e, int64_t *unknowns, int64_t *launches, int *path);
 
 /* Fused Processor-level reset (EquProcessor.reset, fpie/process.py:192-271)

@@ -409,3 +409,49 @@ def test_gather_long_runs_replay_a_cuda_graph(generic, monkeypatch):
     plain.reset(n, A, X, B)
     plain.step(361)
     np.testing.assert_array_equal(plain.state(), want)
+
+
+def test_gather_table_forms_are_bit_identical(monkeypatch):
+    """The structured gather path streams 34 bytes per unknown and sweep (4-byte distance table + fp16 B) when the
+    system allows it, 40 (fp32 B) when some B is not exactly a half, 44 (8-byte table) when a neighbour is further
+    than 32767 ids away -- all with the reference's operands and add order: same bits."""
+    import fpie_b200
+    from fpie_b200 import synth
+
+    src, mask, tgt = synth.make_problem("ring", 700, 900, seed=4)
+    n, A, X, B, _ = np_oracle.equ_system(src, mask, tgt, (0, 0), (0, 0), "avg")
+    want = c_oracle.equ_sweeps(A, X, B, 77)
+    # by default only systems beyond the L2 (>= 2^21 unknowns) take the 4-byte table: small ones are faster with one
+    # unknown per thread
+    d = fpie_b200.EquSolver(256, mode="gather")
+    d.reset(n, A, X, B)
+    assert d.info()["table"] == "int2 + fp32 B"
+    monkeypatch.setenv("FPIE_B200_DELTA16_MIN", "0")
+    s = fpie_b200.EquSolver(256, mode="gather")
+    s.reset(n, A, X, B)
+    assert s.info()["path"] == "gather-compact" and s.info()["table"] == "delta16 + fp16 B"
+    s.step(77)
+    np.testing.assert_array_equal(s.state(), want)
+    # B that is not representable in fp16 (a legal system: B is just numbers): the fp32 stream, same bits
+    B2 = B.copy()
+    B2[5, 1] += np.float32(0.001)
+    B2[n // 2, 2] = np.float32(70000.25)
+    s.reset(n, A, X, B2)
+    assert s.info()["table"] == "delta16 + fp32 B"
+    s.step(40)
+    np.testing.assert_array_equal(s.state(), c_oracle.equ_sweeps(A, X, B2, 40))
+    # the 8-byte table when asked for (and the distance check: a system whose up-neighbours are far away)
+    monkeypatch.setenv("FPIE_B200_NO_DELTA16", "1")
+    t = fpie_b200.EquSolver(256, mode="gather")
+    t.reset(n, A, X, B)
+    assert t.info()["table"] == "int2 + fp32 B"
+    t.step(77)
+    np.testing.assert_array_equal(t.state(), want)
+    monkeypatch.delenv("FPIE_B200_NO_DELTA16")
+    wide_src, wide_mask, wide_tgt = synth.make_problem("square", 6, 40000, seed=1)  # rows of 39998 unknowns
+    nw, Aw, Xw, Bw, _ = np_oracle.equ_system(wide_src, wide_mask, wide_tgt, (0, 0), (0, 0), "max")
+    w = fpie_b200.EquSolver(256, mode="gather")
+    w.reset(nw, Aw, Xw, Bw)
+    assert w.info()["table"] == "int2 + fp32 B"
+    w.step(9)
+    np.testing.assert_array_equal(w.state(), c_oracle.equ_sweeps(Aw, Xw, Bw, 9))
