@@ -30,12 +30,41 @@ from .solver import EquSolver, GridSolver
 BACKEND = b200_process.BACKEND
 
 
-def register(fused: bool = True, make_default: bool = False):
-    """Patch ``fpie`` in place; returns ``(EquProcessor, GridProcessor)`` dispatchers."""
+def _stage_io() -> None:
+    """Rebind ``fpie.io.read_images`` / ``write_image`` (and the names ``fpie.cli`` / ``fpie.gui`` imported,
+    cli.py:6) to this package's versions: concurrent decode into page-locked staging buffers, PNG encoding in
+    a worker thread (``fpie_b200.io``).  Same arrays, same files."""
+    import sys
+
+    import fpie.io as fio
+
+    from . import io as b200_io
+
+    if getattr(fio, "_b200_staged", False):
+        return
+    fio.read_image, fio.read_images = b200_io.read_image, b200_io.read_images
+    fio.write_image = b200_io.write_image_async
+    for name in ("fpie.cli", "fpie.gui"):
+        mod = sys.modules.get(name)
+        if mod is not None:
+            for attr in ("read_images", "read_image"):
+                if hasattr(mod, attr):
+                    setattr(mod, attr, getattr(fio, attr))
+            if hasattr(mod, "write_image"):
+                mod.write_image = fio.write_image
+    fio._b200_staged = True
+
+
+def register(fused: bool = True, make_default: bool = False, stage_io: bool = False):
+    """Patch ``fpie`` in place; returns ``(EquProcessor, GridProcessor)`` dispatchers.  ``stage_io`` also
+    swaps the image I/O helpers for the staged ones (callers must ``fpie_b200.io.flush_writes()`` before
+    reading what was written; interpreter exit does it too)."""
     import sys
 
     import fpie.process as fp
 
+    if stage_io:
+        _stage_io()
     if getattr(fp, "_b200_registered", False):
         return fp.EquProcessor, fp.GridProcessor
     if BACKEND not in fp.ALL_BACKEND:
@@ -86,10 +115,15 @@ def register(fused: bool = True, make_default: bool = False):
 
 def main() -> None:
     """``python -m fpie_b200.register [fpie CLI flags]`` == ``fpie`` with ``-b b200`` available."""
-    register()
+    register(stage_io=True)
     from fpie.cli import main as fpie_main
 
-    fpie_main()
+    from .io import flush_writes
+
+    try:
+        fpie_main()
+    finally:
+        flush_writes()
 
 
 def gui_main() -> None:

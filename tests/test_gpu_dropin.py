@@ -28,7 +28,7 @@ import contextlib, io, json, os, sys
 mode, jobs = sys.argv[1], json.loads(sys.argv[2])
 if mode != "stock":
     import fpie_b200
-    fpie_b200.register(fused=(mode == "fused"))
+    fpie_b200.register(fused=(mode != "core"), stage_io=(mode == "staged"))
 from fpie.cli import main
 logs = {}
 for name, cwd, argv in jobs:
@@ -37,6 +37,9 @@ for name, cwd, argv in jobs:
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
         main()
+    if mode == "staged":
+        import fpie_b200.io
+        fpie_b200.io.flush_writes()  # (python -m fpie_b200.register does this itself)
     logs[name] = buf.getvalue()
 print(json.dumps(logs))
 """
@@ -81,7 +84,8 @@ CASES = [
     ("equ", "avg", "holes", 64, 80),
 ]
 OFFSET_FLAGS = ["-n", "90", "-p", "30", "-h0", "12", "-w0", "20", "-h1", "40", "-w1", "55"]
-MODES3 = (("stock", "numpy"), ("fused", "b200"), ("core", "b200"))
+# "staged": the fused wiring with fpie.io swapped for fpie_b200.io (page-locked staging, PNG encoding in a worker)
+MODES3 = (("stock", "numpy"), ("fused", "b200"), ("core", "b200"), ("staged", "b200"))
 
 
 @pytest.fixture(scope="module")
@@ -139,7 +143,7 @@ def test_cli_b200_equals_cli_numpy(cli_runs, method, gradient, kind, h, w, wirin
         np.testing.assert_allclose(b, a, rtol=1e-4)
 
 
-@pytest.mark.parametrize("wiring", ["fused", "core"])
+@pytest.mark.parametrize("wiring", ["fused", "core", "staged"])
 @pytest.mark.parametrize("method", ["grid", "equ"])
 def test_cli_offsets_progress_images_and_soft_mask(cli_runs, method, wiring):
     """`-h0/-w0/-h1/-w1` offsets, `-p` progress images (cli.py:48-57: repeated step calls on one
