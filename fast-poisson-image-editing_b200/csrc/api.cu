@@ -330,6 +330,26 @@ API int fpie_b200_equ_info(fpie_b200_equ *e, int64_t *unknowns, int64_t *launche
     if (path) *path = e->impl.path();
   });
 }
+API int fpie_b200_equ_set_window(fpie_b200_equ *e, int64_t lo, int64_t hi) {
+  NEED(e);
+  return guarded([&] { e->impl.set_window(lo, hi); });
+}
+API int fpie_b200_equ_fetch_rows(fpie_b200_equ *e, int64_t lo, int64_t hi, uint8_t *out_img, float *out_err3) {
+  NEED(e);
+  return guarded([&] { e->impl.fetch_rows(lo, hi, out_img, out_err3); });
+}
+API int fpie_b200_equ_gather_rows(fpie_b200_equ *e, const int32_t *dev_idx, int64_t n, float *dev_out) {
+  NEED(e);
+  return guarded([&] { e->impl.gather_rows(dev_idx, n, dev_out); });
+}
+API int fpie_b200_equ_scatter_rows(fpie_b200_equ *e, const int32_t *dev_idx, int64_t n, const float *dev_in) {
+  NEED(e);
+  return guarded([&] { e->impl.scatter_rows(dev_idx, n, dev_in); });
+}
+API int fpie_b200_equ_rows_checked(fpie_b200_equ *e, int on) {
+  NEED(e);
+  return guarded([&] { e->impl.set_rows_checked(on != 0); });
+}
 API int fpie_b200_equ_reset_from_images(fpie_b200_equ *e, const uint8_t *src, int sh, int sw, const uint8_t *mask,
                                         int mh, int mw, int mc, const uint8_t *tgt, int th, int tw, int h0, int w0,
                                         int h1, int w1, int grad_mode, int64_t *out_n, int32_t *out_box4) {

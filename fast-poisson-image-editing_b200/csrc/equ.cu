@@ -347,9 +347,10 @@ __global__ void rb_combine_kernel(const int32_t *__restrict__ mask, long long co
 
 // err[c] = sum_i |((((B + X[up]) + X[down]) + X[left]) + X[right]) - 4 X[i]|   (np_solver.py:42-50)
 __global__ void __launch_bounds__(256)
-equ_residual_kernel(long long N, long long pitch, const int4 *__restrict__ A, const float *__restrict__ B,
-                    const float *__restrict__ x, double *__restrict__ err) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+equ_residual_kernel(long long lo, long long N, long long pitch, const int4 *__restrict__ A,
+                    const float *__restrict__ B, const float *__restrict__ x, double *__restrict__ err) {
+  // rows [lo, N): the whole system, or the rows a rank owns of an id-range shard (set_window)
+  const long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x;
   double v[3] = {0.0, 0.0, 0.0};
   if (i < N) {
     const int4 a = A[i];
@@ -393,6 +394,37 @@ equ_to_u8_kernel(long long N, long long pitch, const float *__restrict__ x, uint
   if (i >= N) return;
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) img[i * 3 + ch] = clip_byte(x[ch * pitch + i]);
+}
+
+// Rows of X by index, packed [n, 3]: the data plane of the id-range sharded solver (fpie_b200/shard.py) -- what a
+// rank sends are the rows its peers hold as ghosts, what it receives lands in its own ghost rows.  The reference's
+// MPI EquSolver moves ALL of X through rank 0 instead (mpi/equ.cc:136-146).
+__global__ void __launch_bounds__(256)
+equ_gather_rows_kernel(long long n, long long N, long long pitch, const int32_t *__restrict__ idx,
+                       const float *__restrict__ x, float *__restrict__ out, int *__restrict__ bad) {
+  const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const long long i = idx[j];
+  if (i < 0 || i >= N) {
+    atomicExch(bad, 1);
+    return;
+  }
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) out[j * 3 + ch] = x[ch * pitch + i];
+}
+
+__global__ void __launch_bounds__(256)
+equ_scatter_rows_kernel(long long n, long long N, long long pitch, const int32_t *__restrict__ idx,
+                        const float *__restrict__ in, float *__restrict__ x, int *__restrict__ bad) {
+  const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const long long i = idx[j];
+  if (i <= 0 || i >= N) {  // (row 0 is the constant: never a ghost)
+    atomicExch(bad, 1);
+    return;
+  }
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) x[ch * pitch + i] = in[j * 3 + ch];
 }
 
 // ---------------------------------------------------------------------------
@@ -576,6 +608,9 @@ void EquSolver::allocate(int64_t N) {
   B_.resize((size_t)pitch_ * 3);
   img_.resize((size_t)N * 3);
   cur_ = 0;
+  win_lo_ = 0;
+  win_hi_ = N;
+  rows_checked_ = false;
 }
 
 void EquSolver::reset(int64_t N, const int32_t *A, const float *X, const float *B) {
@@ -830,7 +865,8 @@ void EquSolver::finish_async() {
   DeviceGuard guard(device_);
   pull_tiled_state();
   CUDA_CHECK(cudaMemsetAsync(err_.ptr, 0, 3 * sizeof(double), stream_));
-  equ_residual_kernel<<<blocks_for(N_, 256), 256, 0, stream_>>>(N_, pitch_, A_.ptr, B_.ptr, X_[cur_].ptr, err_.ptr);
+  equ_residual_kernel<<<blocks_for(std::max<int64_t>(win_hi_ - win_lo_, 1), 256), 256, 0, stream_>>>(
+      win_lo_, win_hi_, pitch_, A_.ptr, B_.ptr, X_[cur_].ptr, err_.ptr);
   equ_to_u8_kernel<<<blocks_for(N_, 256), 256, 0, stream_>>>(N_, pitch_, X_[cur_].ptr, img_.ptr);
   CUDA_CHECK(cudaGetLastError());
   stats_.launches += 2;
@@ -849,6 +885,59 @@ void EquSolver::fetch(uint8_t *out_img, float *out_err3) {
   CUDA_CHECK(cudaStreamSynchronize(stream_));
   if (out_err3)
     for (int c = 0; c < 3; ++c) out_err3[c] = (float)host_err_[c];
+}
+
+void EquSolver::set_window(int64_t lo, int64_t hi) {
+  require_ready();
+  FPIE_REQUIRE(lo >= 0 && lo <= hi && hi <= N_, "set_window: rows outside [0, N]");
+  win_lo_ = lo;
+  win_hi_ = hi;
+}
+
+void EquSolver::fetch_rows(int64_t lo, int64_t hi, uint8_t *out_img, float *out_err3) {
+  require_ready();
+  FPIE_REQUIRE(lo >= 0 && lo <= hi && hi <= N_, "fetch_rows: rows outside [0, N]");
+  DeviceGuard guard(device_);
+  if (out_img && hi > lo)
+    CUDA_CHECK(cudaMemcpyAsync(out_img, img_.ptr + lo * 3, (size_t)(hi - lo) * 3, cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  if (out_err3)
+    for (int c = 0; c < 3; ++c) out_err3[c] = (float)host_err_[c];
+}
+
+void EquSolver::gather_rows(const int32_t *dev_idx, int64_t n, float *dev_out) {
+  require_ready();
+  FPIE_REQUIRE(n >= 0 && (n == 0 || (dev_idx && dev_out)), "gather_rows: bad arguments");
+  if (n == 0) return;
+  DeviceGuard guard(device_);
+  pull_tiled_state();
+  CUDA_CHECK(cudaMemsetAsync(flag_.ptr, 0, sizeof(int), stream_));
+  equ_gather_rows_kernel<<<blocks_for(n, 256), 256, 0, stream_>>>(n, N_, pitch_, dev_idx, X_[cur_].ptr, dev_out, flag_.ptr);
+  CUDA_CHECK(cudaGetLastError());
+  stats_.launches += 1;
+  check_rows_flag("gather_rows");
+}
+
+void EquSolver::scatter_rows(const int32_t *dev_idx, int64_t n, const float *dev_in) {
+  require_ready();
+  FPIE_REQUIRE(n >= 0 && (n == 0 || (dev_idx && dev_in)), "scatter_rows: bad arguments");
+  FPIE_REQUIRE(!promoted_ && mode_ == 0, "scatter_rows: only the index-mapped Jacobi path takes rows from outside");
+  if (n == 0) return;
+  DeviceGuard guard(device_);
+  CUDA_CHECK(cudaMemsetAsync(flag_.ptr, 0, sizeof(int), stream_));
+  equ_scatter_rows_kernel<<<blocks_for(n, 256), 256, 0, stream_>>>(n, N_, pitch_, dev_idx, dev_in, X_[cur_].ptr, flag_.ptr);
+  CUDA_CHECK(cudaGetLastError());
+  stats_.launches += 1;
+  check_rows_flag("scatter_rows");
+}
+
+// the index check of gather / scatter is read back lazily: at the next call, and by sync() / fetch()
+void EquSolver::check_rows_flag(const char *who) {
+  if (!rows_checked_) {  // the first call with a new index list is checked synchronously
+    CUDA_CHECK(cudaMemcpyAsync(host_flag_, flag_.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaStreamSynchronize(stream_));
+    FPIE_REQUIRE(*host_flag_ == 0, std::string(who) + ": an index is outside the system");
+  }
 }
 
 // Sweep until every channel's residual is <= tol (checked every `check_every` sweeps) or `max_iters`
@@ -884,7 +973,8 @@ void EquSolver::step_paste(int iters, uint8_t *out_crop, float *out_err3, int64_
   sweeps_async(iters);
   pull_tiled_state();
   CUDA_CHECK(cudaMemsetAsync(err_.ptr, 0, 3 * sizeof(double), stream_));
-  equ_residual_kernel<<<blocks_for(N_, 256), 256, 0, stream_>>>(N_, pitch_, A_.ptr, B_.ptr, X_[cur_].ptr, err_.ptr);
+  equ_residual_kernel<<<blocks_for(std::max<int64_t>(win_hi_ - win_lo_, 1), 256), 256, 0, stream_>>>(
+      win_lo_, win_hi_, pitch_, A_.ptr, B_.ptr, X_[cur_].ptr, err_.ptr);
   const int64_t K = N_ - 1;
   if (K > 0)
     equ_paste_kernel<<<blocks_for(K, 256), 256, 0, stream_>>>(K, pitch_, X_[cur_].ptr, pix_.ptr, canvas_.ptr);

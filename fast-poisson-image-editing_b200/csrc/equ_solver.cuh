@@ -35,6 +35,13 @@ class EquSolver {
   void step_paste(int iters, uint8_t *out_crop, float *out_err3, int64_t row_stride = 0);
   void state(float *out);
   void system(int32_t *out_A, float *out_X, float *out_B);
+  // id-range sharding (fpie_b200/shard.py): residual over rows [lo, hi) only; uint8 rows [lo, hi); rows of X by
+  // index, packed [n, 3], to / from DEVICE buffers on the solver's stream
+  void set_window(int64_t lo, int64_t hi);
+  void fetch_rows(int64_t lo, int64_t hi, uint8_t *out_img, float *out_err3);
+  void gather_rows(const int32_t *dev_idx, int64_t n, float *dev_out);
+  void scatter_rows(const int32_t *dev_idx, int64_t n, const float *dev_in);
+  void set_rows_checked(bool on) { rows_checked_ = on; }
 
   const EquStats &stats() const { return stats_; }
   int64_t launches() const { return stats_.launches + (tiled_ ? tiled_->stats().launches : 0); }
@@ -58,6 +65,7 @@ class EquSolver {
   void try_promote(int n, int m);
   void pull_tiled_state();
   void drop_graphs();
+  void check_rows_flag(const char *who);
 
   int device_;
   cudaStream_t stream_;
@@ -66,6 +74,8 @@ class EquSolver {
   int mode_ = 0;        // 0 = Jacobi, 1 = red-black Gauss-Seidel
   int64_t n_mid_ = 0;   // first even id (red-black mode)
   DeviceBuffer<int32_t> rb_tmp_;
+  int64_t win_lo_ = 0, win_hi_ = 0;  // rows the residual sums over (the whole system unless set_window)
+  bool rows_checked_ = false;        // gather / scatter index lists already validated (skip the per-call sync)
   int64_t N_ = 0;      // rows including the constant row 0
   int64_t pitch_ = 0;  // floats per channel plane of X / B
   int cur_ = 0;

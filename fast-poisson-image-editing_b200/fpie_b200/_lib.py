@@ -79,6 +79,11 @@ SIGNATURES = {
     "fpie_b200_equ_step_paste": [c_void_p, c_int, u8p, f32p],
     "fpie_b200_equ_step_paste_into": [c_void_p, c_int, u8p, c_i64, f32p],
     "fpie_b200_equ_system": [c_void_p, i32p, f32p, f32p],
+    "fpie_b200_equ_set_window": [c_void_p, c_i64, c_i64],
+    "fpie_b200_equ_fetch_rows": [c_void_p, c_i64, c_i64, u8p, f32p],
+    "fpie_b200_equ_gather_rows": [c_void_p, c_void_p, c_i64, c_void_p],
+    "fpie_b200_equ_scatter_rows": [c_void_p, c_void_p, c_i64, c_void_p],
+    "fpie_b200_equ_rows_checked": [c_void_p, c_int],
 }
 
 _lib = None

@@ -540,6 +540,33 @@ class EquSolver(_Handle):
         _lib.check(self._lib.fpie_b200_equ_fetch(self.handle, _ptr(img, ctypes.c_uint8), _ptr(err, ctypes.c_float)))
         return img, err
 
+    # -- id-range sharding (fpie_b200/shard.py) ------------------------------------
+    def set_window(self, lo: int, hi: int) -> None:
+        """The residual of ``finish`` / ``step`` sums rows ``[lo, hi)`` only."""
+        _lib.check(self._lib.fpie_b200_equ_set_window(self.handle, int(lo), int(hi)))
+
+    def fetch_rows(self, lo: int, hi: int, img: np.ndarray | None = None):
+        """uint8 rows ``[lo, hi)`` of the last ``finish_async`` and ``err``."""
+        self._need_reset()
+        if img is None:
+            img = np.empty((hi - lo, 3), np.uint8)
+        err = np.empty(3, np.float32)
+        _lib.check(self._lib.fpie_b200_equ_fetch_rows(self.handle, int(lo), int(hi), _ptr(img, ctypes.c_uint8),
+                                                      _ptr(err, ctypes.c_float)))
+        return img, err
+
+    def gather_rows(self, idx_ptr: int, n: int, out_ptr: int) -> None:
+        """``out[j, :] = X[idx[j], :]`` for DEVICE buffers (``idx`` int32, ``out`` fp32 ``[n, 3]``), on the solver's stream."""
+        _lib.check(self._lib.fpie_b200_equ_gather_rows(self.handle, int(idx_ptr), int(n), int(out_ptr)))
+
+    def scatter_rows(self, idx_ptr: int, n: int, in_ptr: int) -> None:
+        """``X[idx[j], :] = in[j, :]`` for DEVICE buffers, on the solver's stream."""
+        _lib.check(self._lib.fpie_b200_equ_scatter_rows(self.handle, int(idx_ptr), int(n), int(in_ptr)))
+
+    def rows_checked(self, on: bool = True) -> None:
+        """The index lists of ``gather_rows`` / ``scatter_rows`` were validated: skip the per-call read-back."""
+        _lib.check(self._lib.fpie_b200_equ_rows_checked(self.handle, int(bool(on))))
+
     def info(self) -> dict:
         unk, launches, path = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int()
         _lib.check(self._lib.fpie_b200_equ_info(self.handle, ctypes.byref(unk), ctypes.byref(launches),

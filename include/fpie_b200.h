@@ -310,6 +310,20 @@ int fpie_b200_equ_step_paste_into(fpie_b200_equ *e, int iters, uint8_t *dst, int
 /* Read back the system built by reset_from_images (parity checks). */
 int fpie_b200_equ_system(fpie_b200_equ *e, int32_t *out_A, float *out_X, float *out_B);
 
+/* Id-range sharding of a general system across devices (fpie_b200/shard.py; the reference's analogue is the MPI
+ * EquSolver, fpie/core/mpi/equ.cc:50-59 offsets and 123-146 the exchange -- which moves ALL of X through rank 0 every
+ * `min_interval` sweeps; here a rank holds its id range plus `depth` layers of ghost unknowns and only those move).
+ *   set_window  the residual of finish / step sums rows [lo, hi) only (the rows this rank owns);
+ *   fetch_rows  the uint8 rows [lo, hi) of the last finish (+ err);
+ *   gather_rows / scatter_rows  rows of X by index, packed [n, 3] fp32, from / into DEVICE buffers (idx: int32 on the
+ *               device), enqueued on the solver's stream.  Indices are validated on the device; the first call after a
+ *               reset reports a bad index synchronously, rows_checked(1) turns the per-call read-back off. */
+int fpie_b200_equ_set_window(fpie_b200_equ *e, int64_t lo, int64_t hi);
+int fpie_b200_equ_fetch_rows(fpie_b200_equ *e, int64_t lo, int64_t hi, uint8_t *out_img, float *out_err3);
+int fpie_b200_equ_gather_rows(fpie_b200_equ *e, const int32_t *dev_idx, int64_t n, float *dev_out);
+int fpie_b200_equ_scatter_rows(fpie_b200_equ *e, const int32_t *dev_idx, int64_t n, const float *dev_in);
+int fpie_b200_equ_rows_checked(fpie_b200_equ *e, int on);
+
 #ifdef __cplusplus
 }
 #endif

@@ -242,3 +242,56 @@ def random_grid(n, m, seed, density=0.7):
     grad = (rng.integers(-2040, 2041, (n, m, 3)) / 2).astype(np.float32)
     grad[mask == 0] = 0
     return mask, tgt, grad
+
+
+class OracleEquShardCore:
+    """Core protocol of ``fpie_b200.shard.ShardedEquSolver`` on the CPU: the local system (owned ids +
+    ghost layers) is swept by the numpy oracle, exactly what ``EquSolver(mode="gather")`` does to it; index
+    lists and message buffers are host tensors."""
+
+    device = torch.device("cpu")
+
+    def partition(self, mask):
+        return np_oracle.partition_rowmajor(np.asarray(mask))
+
+    def reset(self, N, A, X, B):
+        self.A = np.array(A, np.int32, copy=True)
+        self.X = np.array(X, np.float32, copy=True)
+        self.B = np.array(B, np.float32, copy=True)
+        assert self.A.shape == (N, 4) and self.X.shape == (N, 3)
+        self.window = (0, N)
+        self.checked = False
+
+    def set_window(self, lo, hi):
+        self.window = (lo, hi)
+
+    def rows_checked(self, on):
+        self.checked = bool(on)
+
+    def sweeps_async(self, k):
+        self.X = np_oracle.equ_sweeps(self.A, self.X, self.B, int(k))
+
+    def finish_async(self):
+        pass
+
+    def fetch_rows(self, lo, hi):
+        a, b = self.window
+        keep = np.zeros(self.A.shape[0], bool)
+        keep[a:b] = True
+        s = self.B + self.X[self.A[:, 0]] + self.X[self.A[:, 1]] + self.X[self.A[:, 2]] + self.X[self.A[:, 3]] - 4.0 * self.X
+        err = np.abs(s[keep].astype(np.float64)).sum(0)
+        return np_oracle.clip_u8(self.X[lo:hi]), err.astype(np.float32)
+
+    def state(self):
+        return self.X.copy()
+
+    def make_index(self, rows):
+        rows = np.asarray(rows, np.int64)
+        assert rows.size == 0 or (rows.min() >= 1 and rows.max() < self.A.shape[0])
+        return rows
+
+    def gather(self, idx, n):
+        return torch.from_numpy(self.X[idx].copy()).reshape(n, 3)
+
+    def scatter(self, idx, n, rows):
+        self.X[idx] = rows.numpy().reshape(n, 3)
