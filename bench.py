@@ -54,7 +54,9 @@ def equ_kernel_name(info):
     B stream) for row-major systems beyond the L2, 8-byte (up, down) table for smaller ones, int4 table otherwise."""
     if info.get("path") != "gather-compact":
         return "equ_sweep_kernel"
-    return "equ_sweep_d16_kernel" if (info.get("table") or "").startswith("delta16") else "equ_sweep_lr_kernel"
+    if (info.get("table") or "").startswith("delta16"):  # persistent + pipelined unless switched off (A/B)
+        return "equ_sweep_d16_kernel" if os.environ.get("FPIE_B200_D16_PIPE", "")[:1] == "0" else "equ_sweep_d16p_kernel"
+    return "equ_sweep_lr_kernel"
 
 
 def measured_peak():

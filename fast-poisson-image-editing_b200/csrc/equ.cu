@@ -280,6 +280,90 @@ equ_sweep_d16_kernel(long long N, long long pitch, const uint32_t *__restrict__ 
   }
 }
 
+// The 4-byte-table sweep as a PERSISTENT, software-pipelined kernel.  A sweep of equ_sweep_d16_kernel costs the
+// same ~260 us on config 3 as the 8-byte and the 16-byte table kernels although it moves a third less: ncu shows no
+// saturated unit (DRAM 72 %, L2 39 %, L1 wavefronts 74 % -- and halving those with 128-bit gathers made it slower),
+// only warps waiting on memory: a thread's gathers cannot start before its table entry has arrived, two dependent
+// trips to DRAM per unknown.  Here a CTA strides over the system and a thread fetches the table entry and B of its
+// NEXT four unknowns before it gathers for the current four, so the two trips of consecutive chunks overlap:
+// 262 -> 235 us per sweep on config 3 (135 -> 150 Gupd/s, 5.0 TB/s of DRAM traffic).  Measured around it: fetching
+// two chunks ahead helps at equal occupancy (124 -> 142 Gupd/s at three CTAs per SM) but needs 80 registers, and
+// four CTAs per SM with one chunk ahead is faster (150); prefetching the centre vectors as well: 114; half the
+// occupancy: 117 -- the kernel is bound by memory latency x resident warps, under the board's power cap
+// (SM clock 1.6 GHz in these runs).
+template <bool BH>
+__global__ void __launch_bounds__(256, BH ? 4 : 3)
+equ_sweep_d16p_kernel(long long N, long long pitch, const uint32_t *__restrict__ D16, const float *__restrict__ B,
+                      const __half *__restrict__ B16, const float *__restrict__ xin, float *__restrict__ xout) {
+  const long long stride = 4ll * gridDim.x * blockDim.x;
+  long long i0 = 4 * (blockIdx.x * (long long)blockDim.x + threadIdx.x);
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // (see equ_sweep_lr_kernel)
+  if (i0 >= N) return;
+  uint4 tv, tvn = make_uint4(0u, 0u, 0u, 0u);
+  uint2 bh[3], bhn[3];
+  float4 bf[3], bfn[3];
+  auto fetch = [&](long long at, uint4 &t4, uint2 (&h)[3], float4 (&f)[3]) {
+    t4 = *reinterpret_cast<const uint4 *>(D16 + at);  // (the table is zero-padded to the pitch)
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      if (BH)
+        h[ch] = *reinterpret_cast<const uint2 *>(B16 + ch * pitch + at);
+      else
+        f[ch] = ld4(B + ch * pitch + at);
+    }
+  };
+  fetch(i0, tv, bh, bf);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  for (; i0 < N; i0 += stride) {
+    const long long inext = i0 + stride;
+    if (inext < N) fetch(inext, tvn, bhn, bfn);
+    const uint32_t t[4] = {tv.x, tv.y, tv.z, tv.w};
+    int up[4], dn[4];  // (ids are int32: EquSolver::reset requires N < 2^31)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t du = t[j] & 0x7fffu, dd = (t[j] >> 16) & 0x7fffu;
+      up[j] = du ? (int)i0 + j - (int)du : 0;
+      dn[j] = dd ? (int)i0 + j + (int)dd : 0;
+    }
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const float *x = xin + ch * pitch;
+      const float4 cv = ld4(x + i0);
+      const float c[4] = {cv.x, cv.y, cv.z, cv.w};
+      const float zero_row = x[0];  // what an absent neighbour reads (row 0, the constant)
+      float b[4];
+      if (BH) {
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&bh[ch].x));
+        const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&bh[ch].y));
+        b[0] = lo.x, b[1] = lo.y, b[2] = hi.x, b[3] = hi.y;
+      } else {
+        b[0] = bf[ch].x, b[1] = bf[ch].y, b[2] = bf[ch].z, b[3] = bf[ch].w;
+      }
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float lf = (t[j] & 0x8000u) ? (j > 0 ? c[j > 0 ? j - 1 : 0] : x[i0 - 1]) : zero_row;
+        const float rt = (t[j] >> 31) ? (j < 3 ? c[j < 3 ? j + 1 : 3] : x[i0 + 4]) : zero_row;
+        float sum = __fadd_rn(b[j], x[up[j]]);
+        sum = __fadd_rn(sum, x[dn[j]]);
+        sum = __fadd_rn(sum, lf);
+        sum = __fadd_rn(sum, rt);
+        o[j] = __fmul_rn(sum, 0.25f);
+      }
+      if (i0 + 3 < N) {
+        st4(xout + ch * pitch + i0, make_float4(o[0], o[1], o[2], o[3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (i0 + j < N) xout[ch * pitch + i0 + j] = o[j];
+      }
+    }
+    tv = tvn;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) bh[ch] = bhn[ch], bf[ch] = bfn[ch];
+  }
+}
+
 // X'[i] = ((((B[i] + X[up]) + X[down]) + X[left]) + X[right]) / 4   (np_solver.py:33-41)
 __global__ void __launch_bounds__(1024)
 equ_sweep_kernel(long long N, long long pitch, const int4 *__restrict__ A, const float *__restrict__ B,
@@ -499,6 +583,11 @@ EquSolver::EquSolver(int device, cudaStream_t stream, int block_size) : device_(
   no_delta16_ = no_d16 && no_d16[0] && no_d16[0] != '0';
   // The 4-byte table pays off when the sweep streams from HBM (config 3: +10 %); an L2-resident system is faster
   // with one unknown per thread (config 1: 5.6 vs 7.1 us per sweep), so small systems keep the 8-byte table.
+  const char *d16_pipe = getenv("FPIE_B200_D16_PIPE");  // A/B: 0 = one launch-wide pass, N = persistent with N CTAs per SM
+  if (d16_pipe && d16_pipe[0]) {
+    d16_pipe_ = d16_pipe[0] != '0';
+    if (d16_pipe_) d16_ctas_per_sm_ = std::max(1, atoi(d16_pipe));
+  }
   const char *d16_min = getenv("FPIE_B200_DELTA16_MIN");
   delta16_min_ = d16_min && d16_min[0] ? atoll(d16_min) : (1ll << 21);
   int count = 0;
@@ -508,6 +597,7 @@ EquSolver::EquSolver(int device, cudaStream_t stream, int block_size) : device_(
   cudaDeviceProp prop{};
   CUDA_CHECK(cudaGetDeviceProperties(&prop, device_));
   FPIE_REQUIRE(prop.major >= 10, "fpie_b200 is built for sm_100a (Blackwell) only");
+  sm_count_ = prop.multiProcessorCount;
   // the reference's -z flag (fpie/args.py block-size, default 1024); we accept
   // any multiple of 32 up to 1024 and default to 256
   if (block_size >= 100000) {  // 100000 + z: block size z, always the generic int4 table (cross-checks)
@@ -805,10 +895,11 @@ void EquSolver::sweeps_async(int iters) {
       const __half *b16 = b16_.ptr;
       cfg.blockDim = dim3(256);
       cfg.gridDim = dim3((unsigned)blocks_for((N_ + 3) / 4, 256));
-      if (b16_ok_)
-        CUDA_CHECK(cudaLaunchKernelEx(&cfg, equ_sweep_d16_kernel<true>, (long long)N_, (long long)pitch_, d16, b, b16, xin, xout));
-      else
-        CUDA_CHECK(cudaLaunchKernelEx(&cfg, equ_sweep_d16_kernel<false>, (long long)N_, (long long)pitch_, d16, b, b16, xin, xout));
+      auto kern = d16_pipe_ ? (b16_ok_ ? equ_sweep_d16p_kernel<true> : equ_sweep_d16p_kernel<false>)
+                            : (b16_ok_ ? equ_sweep_d16_kernel<true> : equ_sweep_d16_kernel<false>);
+      if (d16_pipe_)  // persistent: d16_ctas_per_sm_ CTAs per SM stride over the system
+        cfg.gridDim = dim3((unsigned)std::min<long long>(cfg.gridDim.x, (long long)sm_count_ * std::min(d16_ctas_per_sm_, b16_ok_ ? 4 : 3)));
+      CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, (long long)N_, (long long)pitch_, d16, b, b16, xin, xout));
     } else if (structured_) {
       const int2 *ud = ud_.ptr;
       CUDA_CHECK(cudaLaunchKernelEx(&cfg, equ_sweep_lr_kernel, (long long)N_, (long long)pitch_, ud, b, xin, xout));

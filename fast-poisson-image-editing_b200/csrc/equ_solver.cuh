@@ -84,6 +84,9 @@ class EquSolver {
   DeviceBuffer<uint32_t> d16_; // 4-byte table: 15-bit distances to up / down + presence bits
   DeviceBuffer<__half> b16_;   // fp16 copy of B (streamed when every value is exactly representable)
   bool delta16_ = false, b16_ok_ = false, no_delta16_ = false;
+  bool d16_pipe_ = true;  // persistent, software-pipelined form of the 4-byte-table kernel
+  int d16_ctas_per_sm_ = 4;
+  int sm_count_ = 148;
   long long delta16_min_ = 1ll << 21;  // unknowns from which the 4-byte table is used (working set beyond the L2)
   bool structured_ = false;    // left/right are always i-1 / i+1 or absent
   bool force_generic_ = false;

@@ -432,6 +432,19 @@ def test_gather_table_forms_are_bit_identical(monkeypatch):
     assert s.info()["path"] == "gather-compact" and s.info()["table"] == "delta16 + fp16 B"
     s.step(77)
     np.testing.assert_array_equal(s.state(), want)
+    # the one-pass form of the same kernel (A/B switch; the default is persistent and software-pipelined)
+    monkeypatch.setenv("FPIE_B200_D16_PIPE", "0")
+    one = fpie_b200.EquSolver(256, mode="gather")
+    one.reset(n, A, X, B)
+    assert one.info()["table"] == "delta16 + fp16 B"
+    one.step(77)
+    np.testing.assert_array_equal(one.state(), want)
+    monkeypatch.setenv("FPIE_B200_D16_PIPE", "1")  # one CTA per SM: every thread strides over many chunks
+    few = fpie_b200.EquSolver(256, mode="gather")
+    few.reset(n, A, X, B)
+    few.step(77)
+    np.testing.assert_array_equal(few.state(), want)
+    monkeypatch.delenv("FPIE_B200_D16_PIPE")
     # B that is not representable in fp16 (a legal system: B is just numbers): the fp32 stream, same bits
     B2 = B.copy()
     B2[5, 1] += np.float32(0.001)
