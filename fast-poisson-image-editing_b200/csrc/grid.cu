@@ -1508,8 +1508,8 @@ void GridSolver::patch_sweeps(int iters) {
   a.stream = stream_;
   // every pixel but the 1-pixel frame of every patch is an unknown, and the patch fills the cluster's rows and
   // the warp's columns exactly: the select-free instruction stream
-  const bool frame = stats_.unknowns == (int64_t)a.bm.batch * (a.bm.ph - 2) * (a.bm.pw - 2) &&
-                     a.bm.ph == cl * 8 * r && a.bm.pw == 32 * cpt;
+  const bool all_unknown = stats_.unknowns == (int64_t)a.bm.batch * (a.bm.ph - 2) * (a.bm.pw - 2);
+  const bool frame = all_unknown && a.bm.ph == cl * 8 * r && a.bm.pw == 32 * cpt;
   if (r == 4 && cpt == 8)
     patch_clusters_ = launch_patch_f<4, 8>(a, frame);
   else if (r == 8 && cpt == 8)

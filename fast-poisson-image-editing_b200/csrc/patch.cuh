@@ -118,25 +118,51 @@ __device__ __forceinline__ void patch_row_update(RowVec<CPT> &xi, const RowVec<C
   }
 }
 
-// Mailbox of one CTA: [parity][slot][lane], slot 0..NW-1 = top rows of the warps, NW..2NW-1 = bottom rows,
-// 2NW = bottom row of the CTA above (written remotely), 2NW+1 = top row of the CTA below (written remotely).
+// Mailbox of one CTA: [parity][slot][16-byte column group][lane] -- a warp's 128-bit accesses to one (slot, group)
+// are 512 contiguous bytes, conflict-free (a [slot][lane] array of 32-byte rows costs two wavefronts per access).
+// slot 0..NW-1 = top rows of the warps, NW..2NW-1 = bottom rows, 2NW = bottom row of the CTA above (written
+// remotely), 2NW+1 = top row of the CTA below (written remotely).
 template <int NW, int CPT>
 struct PatchSmem {
   static constexpr int SLOTS = 2 * NW + 2;
-  RowVec<CPT> mail[2][SLOTS][32];
+  float4 mail[2][SLOTS][CPT / 4][32];
   uint64_t bar[2];
 };
 
+// a predicated st.async (see st_async_cluster4): warps that have no neighbour CTA in that direction issue it with a
+// false predicate instead of branching around it
+__device__ __forceinline__ void st_async_cluster4_if(uint32_t addr, float4 v, uint32_t remote_bar, uint32_t on) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.u32 p, %6, 0;\n"
+      "@p st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];\n"
+      "}\n" ::"r"(addr),
+      "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(remote_bar), "r"(on)
+      : "memory");
+}
+
 // FRAME: every pixel of every patch is an unknown except the 1-pixel frame (the full-square masks of
-// config 5's throughput run and of any whole-image blend): selects are needed on the first / last column
-// only.  Otherwise the per-pixel mask bits select (arbitrary masks, same results).
+// config 5's throughput run and of any whole-image blend): the interior rows of a strip run a select-free
+// stream with two thread-constant column predicates; the strip's first / last row -- which may be the patch's
+// first / last row, never updated -- take per-pixel selects from a thread-constant mask.  Otherwise the
+// per-pixel mask bits select everywhere (arbitrary masks, same results).
+//
+// The sweep loop is branch-free apart from the barrier spin: where a strip's neighbour rows come from (the
+// next warp's slot, the slot a neighbour CTA writes, or -- at the patch's edge, where the row is never used -- the
+// warp's own slot) is an address computed once, the rows for the neighbour CTAs leave through predicated
+// st.async, and the loop is unrolled twice so that the register rotation at its back edge is paid every other
+// sweep.  (Before: 399 issued instructions per warp and sweep for 256 FFMA, 8 % of the samples resolving
+// branches, two-way bank conflicts on every mailbox access -- profiles/r02_patch_ncu_full_summary.txt.)
 template <int R, int NW, int CPT, bool FRAME>
 __global__ void __launch_bounds__(NW * 32, (R <= 4) ? 2 : 1)
 grid_patch_kernel(PlaneGeom g, BatchMap bm, float *__restrict__ x, const float *__restrict__ hq,
                   const uint32_t *__restrict__ bits, int nsweeps, int nitems) {
+  static_assert(R >= 2 && NW >= 2, "a strip has a first and a last row; a CTA has a first and a last warp");
   extern __shared__ __align__(16) unsigned char patch_smem_raw[];
   using S = PatchSmem<NW, CPT>;
   S &sm = *reinterpret_cast<S *>(patch_smem_raw);
+  constexpr int Q = CPT / 4;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int crank = (int)cluster_ctarank(), csize = (int)cluster_nctarank();
   const bool has_up = crank > 0, has_dn = crank + 1 < csize;
@@ -147,22 +173,37 @@ grid_patch_kernel(PlaneGeom g, BatchMap bm, float *__restrict__ x, const float *
   }
   cluster_sync_all();  // every CTA's barriers exist before anyone arrives remotely
 
-  // remote addresses: my top row goes to the CTA above (its slot 2NW+1), my bottom row to the CTA below (slot 2NW)
-  const uint32_t mail_base = smem_u32(&sm.mail[0][0][0]);
+  constexpr uint32_t SLOT_BYTES = Q * 32 * 16;
+  constexpr uint32_t PARITY_BYTES = S::SLOTS * SLOT_BYTES;
+  const uint32_t mail_base = smem_u32(&sm.mail[0][0][0][0]);
   const uint32_t bar_base = smem_u32(&sm.bar[0]);
-  constexpr uint32_t ROW_BYTES = sizeof(RowVec<CPT>);
-  constexpr uint32_t PARITY_BYTES = S::SLOTS * 32 * ROW_BYTES;
-  uint32_t rem_mail = 0, rem_bar = 0;
-  if (w == 0 && has_up) {
-    rem_mail = map_to_cta(mail_base + ((2 * NW + 1) * 32 + lane) * ROW_BYTES, crank - 1);
-    rem_bar = map_to_cta(bar_base, crank - 1);
-  } else if (w == NW - 1 && has_dn) {
-    rem_mail = map_to_cta(mail_base + ((2 * NW) * 32 + lane) * ROW_BYTES, crank + 1);
-    rem_bar = map_to_cta(bar_base, crank + 1);
+  // my top row goes to the CTA above (its slot 2NW+1), my bottom row to the CTA below (slot 2NW)
+  const uint32_t send_up = (w == 0 && has_up) ? 1u : 0u, send_dn = (w == NW - 1 && has_dn) ? 1u : 0u;
+  uint32_t rem_mail_up = 0, rem_bar_up = 0, rem_mail_dn = 0, rem_bar_dn = 0;
+  if (send_up) {
+    rem_mail_up = map_to_cta(mail_base + (2 * NW + 1) * SLOT_BYTES + lane * 16, crank - 1);
+    rem_bar_up = map_to_cta(bar_base, crank - 1);
   }
-  // (with NW == 1 a CTA in the middle of a cluster would need both; the launcher never picks NW == 1)
+  if (send_dn) {
+    rem_mail_dn = map_to_cta(mail_base + (2 * NW) * SLOT_BYTES + lane * 16, crank + 1);
+    rem_bar_dn = map_to_cta(bar_base, crank + 1);
+  }
+  // where the rows above / below this warp's strip are read from (byte offsets inside a parity block)
+  const int up_slot = (w > 0) ? NW + w - 1 : (has_up ? 2 * NW : w);
+  const int dn_slot = (w + 1 < NW) ? w + 1 : (has_dn ? 2 * NW + 1 : NW + w);
+  const uint32_t my_top = mail_base + w * SLOT_BYTES + lane * 16, my_bot = mail_base + (NW + w) * SLOT_BYTES + lane * 16;
+  const uint32_t up_src = mail_base + up_slot * SLOT_BYTES + lane * 16, dn_src = mail_base + dn_slot * SLOT_BYTES + lane * 16;
+  const uint32_t remote_bytes = ((has_up ? 1u : 0u) + (has_dn ? 1u : 0u)) * SLOT_BYTES;
+  const bool arms = (w == 0 && remote_bytes != 0u);
+  auto sts4 = [](uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  };
+  auto lds4 = [](uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+  };
 
-  const uint32_t remote_bytes = ((has_up ? 1u : 0u) + (has_dn ? 1u : 0u)) * 32u * ROW_BYTES;
   int parity = 0;
   uint32_t mphase = 0;
   const int rows_per_cta = NW * R;
@@ -180,7 +221,7 @@ grid_patch_kernel(PlaneGeom g, BatchMap bm, float *__restrict__ x, const float *
     for (int i = 0; i < R; ++i) {
       const bool in = col_in && (r0 + i) < bm.ph;
 #pragma unroll
-      for (int q = 0; q < CPT / 4; ++q) {
+      for (int q = 0; q < Q; ++q) {
         const bool inq = in && (c0 + 4 * q) < bm.pw;
         xr[i].v[q] = inq ? ld4(x + base + (long long)i * g.pitch + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
         hr[i].v[q] = inq ? ld4(hq + base + (long long)i * g.pitch + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -198,33 +239,32 @@ grid_patch_kernel(PlaneGeom g, BatchMap bm, float *__restrict__ x, const float *
       sel[i] = s;
     }
 
-    // FRAME (launcher guarantees ph == cluster rows, pw == 32 * CPT): thread-constant column predicates and
-    // warp-uniform row conditions replace the per-pixel mask
+    // FRAME (launcher guarantees ph == cluster rows, pw == 32 * CPT): thread-constant column predicates for the
+    // interior rows of a strip; the strip's first / last row take the mask bits (all clear on the patch's first /
+    // last row, the frame columns clear elsewhere -- exactly what was loaded into sel[0] / sel[R-1])
     const uint32_t fsel = (lane == 0 ? 1u : 0u) | (lane == 31 ? 2u : 0u);
-    const bool top_frame = !has_up && w == 0, bottom_frame = !has_dn && w == NW - 1;
+#pragma unroll 2
     for (int sw = 0; sw < nsweeps; ++sw) {
-      RowVec<CPT>(*mail)[32] = sm.mail[parity];
+      const uint32_t poff = (uint32_t)parity * PARITY_BYTES;
       uint64_t *bar = &sm.bar[parity];
-      mail[w][lane] = xr[0];
-      mail[NW + w][lane] = xr[R - 1];
-      if (rem_bar) {  // boundary warp: the row also goes to the neighbour CTA
-        const bool to_up = (w == 0 && has_up);
 #pragma unroll
-        for (int q = 0; q < CPT / 4; ++q) {
-          const float4 a = xr[0].v[q], b = xr[R - 1].v[q];
-          const float4 e = make_float4(to_up ? a.x : b.x, to_up ? a.y : b.y, to_up ? a.z : b.z, to_up ? a.w : b.w);
-          st_async_cluster4(rem_mail + parity * PARITY_BYTES + q * 16, e, rem_bar + parity * 8);
-        }
+      for (int q = 0; q < Q; ++q) {
+        sts4(my_top + poff + q * 512, xr[0].v[q]);
+        sts4(my_bot + poff + q * 512, xr[R - 1].v[q]);
+        // boundary warps: the row also goes to the neighbour CTA (data + notification in one message)
+        st_async_cluster4_if(rem_mail_up + poff + q * 512, xr[0].v[q], rem_bar_up + parity * 8, send_up);
+        st_async_cluster4_if(rem_mail_dn + poff + q * 512, xr[R - 1].v[q], rem_bar_dn + parity * 8, send_dn);
       }
       __syncwarp();
       if (lane == 0) {
         // warp 0 also announces the bytes the neighbour CTAs store into this CTA's mailbox in this phase
-        if (w == 0 && remote_bytes)
+        if (arms)
           mbar_expect_tx(bar, remote_bytes);
         else
           mbar_arrive(bar);
       }
-      const RowVec<CPT> first_old = xr[(R > 1) ? 1 : 0];
+      __syncwarp();
+      const RowVec<CPT> first_old = xr[1];
       RowVec<CPT> prev = xr[0];
 #pragma unroll
       for (int i = 1; i < R - 1; ++i) {
@@ -235,33 +275,21 @@ grid_patch_kernel(PlaneGeom g, BatchMap bm, float *__restrict__ x, const float *
       mbar_wait(bar, (mphase >> parity) & 1u);
       mphase ^= 1u << parity;
       RowVec<CPT> up, dn;
-      if (w > 0)
-        up = mail[NW + w - 1][lane];
-      else if (has_up)
-        up = mail[2 * NW][lane];
-      else
-        up = xr[0];  // first row of the patch: frame, never an unknown
-      if (w + 1 < NW)
-        dn = mail[w + 1][lane];
-      else if (has_dn)
-        dn = mail[2 * NW + 1][lane];
-      else
-        dn = xr[R - 1];
-      // FRAME: the patch's first / last row (a warp-uniform condition) is never updated
-      if (R > 1) {
-        if (!FRAME || !top_frame) patch_row_update<CPT, FRAME>(xr[0], hr[0], up, first_old, FRAME ? fsel : sel[0]);
-        if (!FRAME || !bottom_frame)
-          patch_row_update<CPT, FRAME>(xr[R - 1], hr[R - 1], prev, dn, FRAME ? fsel : sel[R - 1]);
-      } else {
-        if (!FRAME || !(top_frame || bottom_frame)) patch_row_update<CPT, FRAME>(xr[0], hr[0], up, dn, FRAME ? fsel : sel[0]);
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        up.v[q] = lds4(up_src + poff + q * 512);
+        dn.v[q] = lds4(dn_src + poff + q * 512);
       }
+      // (at the patch's first / last row `up` / `dn` is the strip's own row: never used, those rows have no unknowns)
+      patch_row_update<CPT, false>(xr[0], hr[0], up, first_old, sel[0]);
+      patch_row_update<CPT, false>(xr[R - 1], hr[R - 1], prev, dn, sel[R - 1]);
       parity ^= 1;
     }
 
 #pragma unroll
     for (int i = 0; i < R; ++i) {
 #pragma unroll
-      for (int q = 0; q < CPT / 4; ++q) {
+      for (int q = 0; q < Q; ++q) {
         const uint32_t nib = (sel[i] >> (4 * q)) & 0xFu;
         if (nib) st4(x + base + (long long)i * g.pitch + 4 * q, xr[i].v[q]);
       }
