@@ -118,6 +118,37 @@ __device__ __forceinline__ void patch_row_update(RowVec<CPT> &xi, const RowVec<C
   }
 }
 
+// patch_row_update with the left / right neighbour values handed in: a sweep's shuffles depend on OLD values only,
+// so the kernel issues all of them at the top of the sweep (one convergence check for the lot instead of one in
+// front of every row's pair, and none behind the barrier)
+template <int CPT, bool FRAME>
+__device__ __forceinline__ void patch_row_update_lr(RowVec<CPT> &xi, const RowVec<CPT> &hi, const RowVec<CPT> &prev,
+                                                    const RowVec<CPT> &nxt, uint32_t sel, float lf, float rt) {
+  const RowVec<CPT> cur = xi;
+#pragma unroll
+  for (int q = 0; q < CPT / 4; ++q) {
+    const float4 c = cur.v[q], h = hi.v[q], u = prev.v[q], d = nxt.v[q];
+    const float left = (q == 0) ? lf : cur.v[q > 0 ? q - 1 : 0].w;
+    const float right = (q == CPT / 4 - 1) ? rt : cur.v[q + 1 < CPT / 4 ? q + 1 : q].x;
+    float4 o;
+    o.x = jacobi_q(h.x, u.x, d.x, left, c.y);
+    o.y = jacobi_q(h.y, u.y, d.y, c.x, c.z);
+    o.z = jacobi_q(h.z, u.z, d.z, c.y, c.w);
+    o.w = jacobi_q(h.w, u.w, d.w, c.z, right);
+    if (!FRAME) {
+      const uint32_t nib = sel >> (4 * q);
+      o.x = (nib & 1u) ? o.x : c.x;
+      o.y = (nib & 2u) ? o.y : c.y;
+      o.z = (nib & 4u) ? o.z : c.z;
+      o.w = (nib & 8u) ? o.w : c.w;
+    } else {
+      if (q == 0) o.x = (sel & 1u) ? c.x : o.x;
+      if (q == CPT / 4 - 1) o.w = (sel & 2u) ? c.w : o.w;
+    }
+    xi.v[q] = o;
+  }
+}
+
 // Mailbox of one CTA: [parity][slot][16-byte column group][lane] -- a warp's 128-bit accesses to one (slot, group)
 // are 512 contiguous bytes, conflict-free (a [slot][lane] array of 32-byte rows costs two wavefronts per access).
 // slot 0..NW-1 = top rows of the warps, NW..2NW-1 = bottom rows, 2NW = bottom row of the CTA above (written
@@ -243,6 +274,7 @@ grid_patch_kernel(PlaneGeom g, BatchMap bm, float *__restrict__ x, const float *
     // interior rows of a strip; the strip's first / last row take the mask bits (all clear on the patch's first /
     // last row, the frame columns clear elsewhere -- exactly what was loaded into sel[0] / sel[R-1])
     const uint32_t fsel = (lane == 0 ? 1u : 0u) | (lane == 31 ? 2u : 0u);
+    const bool top_frame = !has_up && w == 0, bottom_frame = !has_dn && w == NW - 1;
 #pragma unroll 2
     for (int sw = 0; sw < nsweeps; ++sw) {
       const uint32_t poff = (uint32_t)parity * PARITY_BYTES;
@@ -264,12 +296,18 @@ grid_patch_kernel(PlaneGeom g, BatchMap bm, float *__restrict__ x, const float *
           mbar_arrive(bar);
       }
       __syncwarp();
+      float lf[R], rt[R];
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        lf[i] = __shfl_up_sync(0xffffffffu, xr[i].v[Q - 1].w, 1);
+        rt[i] = __shfl_down_sync(0xffffffffu, xr[i].v[0].x, 1);
+      }
       const RowVec<CPT> first_old = xr[1];
       RowVec<CPT> prev = xr[0];
 #pragma unroll
       for (int i = 1; i < R - 1; ++i) {
         const RowVec<CPT> cur = xr[i];
-        patch_row_update<CPT, FRAME>(xr[i], hr[i], prev, xr[i + 1], FRAME ? fsel : sel[i]);
+        patch_row_update_lr<CPT, FRAME>(xr[i], hr[i], prev, xr[i + 1], FRAME ? fsel : sel[i], lf[i], rt[i]);
         prev = cur;
       }
       mbar_wait(bar, (mphase >> parity) & 1u);
@@ -281,8 +319,15 @@ grid_patch_kernel(PlaneGeom g, BatchMap bm, float *__restrict__ x, const float *
         dn.v[q] = lds4(dn_src + poff + q * 512);
       }
       // (at the patch's first / last row `up` / `dn` is the strip's own row: never used, those rows have no unknowns)
-      patch_row_update<CPT, false>(xr[0], hr[0], up, first_old, sel[0]);
-      patch_row_update<CPT, false>(xr[R - 1], hr[R - 1], prev, dn, sel[R - 1]);
+      if (FRAME) {
+        // the patch's first / last row (a warp-uniform condition) is never updated; every other strip edge is an
+        // ordinary row of the select-free stream
+        if (!top_frame) patch_row_update_lr<CPT, true>(xr[0], hr[0], up, first_old, fsel, lf[0], rt[0]);
+        if (!bottom_frame) patch_row_update_lr<CPT, true>(xr[R - 1], hr[R - 1], prev, dn, fsel, lf[R - 1], rt[R - 1]);
+      } else {
+        patch_row_update_lr<CPT, false>(xr[0], hr[0], up, first_old, sel[0], lf[0], rt[0]);
+        patch_row_update_lr<CPT, false>(xr[R - 1], hr[R - 1], prev, dn, sel[R - 1], lf[R - 1], rt[R - 1]);
+      }
       parity ^= 1;
     }
 
