@@ -1473,15 +1473,22 @@ bool GridSolver::patch_shape(int *rows_per_thread, int *cols_per_thread, int *cl
   const bool single = batch_.batch == 0;
   const int ph = single ? geom_.n : batch_.ph, pw = single ? geom_.m : batch_.pw;
   if (pw > 256 || ph > 512) return false;
-  // Measured on B200 (tools/patch_bench.py, profiles/r02_patch_bench.json): a sweep of the persistent kernel is
-  // bound by the per-sweep hand-over between the CTAs of a cluster (0.6-0.75 us), not by arithmetic, so it pays
-  // once enough (patch, plane) items run side by side: 12 patches of 256^2 -> 530 vs 445 Gupd/s for the mosaic
-  // through the tiled kernel, 512 patches -> 948 vs 807; ONE 256^2 image is faster on the tiled kernel (125 vs 107).
+  // Measured on B200 (tools/patch_bench.py, profiles/r02_patch_bench_v2.json).  A sweep of the persistent kernel costs
+  // 0.53 us per cluster with 8 rows per thread (a 256-row plane on 4 CTAs) and 0.42 us with 4 (8 CTAs), whatever the
+  // number of items as long as all clusters are resident; the tiled kernel needs 0.52 us per sweep for ONE 256^2
+  // image and 0.79 us for three.  So: 4 rows per thread while every item's cluster fits the device at once (two
+  // such CTAs per SM), 8 rows per thread -- half the hand-overs per pixel -- for larger batches (512 patches of
+  // 256^2: 1336 vs 1123 Gupd/s; the tiled kernel: 809); one full-square 256^2 image: 155 vs 125 Gupd/s, 128^2: 61 vs
+  // 32.  A single image taller than 128 rows with an arbitrary mask (per-pixel selects) stays on the tiled kernel.
   const int items = (single ? 1 : batch_.batch) * 3;
-  if (!patch_force_ && items < 12) return false;
+  const bool all_unknown = stats_.unknowns == (int64_t)(items / 3) * (ph - 2) * (pw - 2);
+  if (!patch_force_ && items < 9 && ph > 128 && !all_unknown) return false;
   const int cpt = pw <= 128 ? 4 : 8;
-  // 8 rows per thread keep a 256-row patch in a cluster of 4 (one CTA per SM); 4 rows per thread for short patches
-  int r = patch_rows_ > 0 ? patch_rows_ : (ph > 128 ? 8 : 4);
+  int r = patch_rows_;
+  if (r == 0) {
+    const long long ctas4 = (long long)items * ceil_div(ph, 32);
+    r = (ph <= 128 || (ceil_div(ph, 32) <= 8 && ctas4 <= 2ll * sm_count_)) ? 4 : 8;
+  }
   if (ceil_div(ph, 8 * r) > 8) r = 8;
   const int cl = (int)ceil_div(ph, 8 * r);
   if (cl > 8) return false;

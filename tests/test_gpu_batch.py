@@ -107,6 +107,7 @@ def _full_batch(b, n, m, seed):
     (2, 300, 256, 37, True),    # 8 rows per thread (more than 256 rows)
     (2, 512, 200, 35, False),   # the tallest supported patch
     (40, 32, 32, 50, False),    # more clusters than the device holds at once: the persistent loop
+    (40, 256, 256, 40, True),   # a batch too large for 4 rows per thread to be resident at once: 8 rows, cluster of 4
 ])
 def test_persistent_kernel_matches_oracle_and_mosaic(b, n, m, iters, full, monkeypatch):
     import fpie_b200
@@ -117,7 +118,10 @@ def test_persistent_kernel_matches_oracle_and_mosaic(b, n, m, iters, full, monke
     proc.reset(src, mask, tgt)
     info = proc.core.patch_info()
     assert info["usable"] and info["cluster"] == -(-n // (8 * info["rows_per_thread"]))
-    assert info["rows_per_thread"] == (8 if n > 128 else 4)
+    # 4 rows per thread (a plane on up to 8 CTAs) while every item's cluster is resident at once, else 8
+    sms = fpie_b200.device_info(0)["sm_count"]
+    cl4 = -(-n // 32)
+    assert info["rows_per_thread"] == (4 if (n <= 128 or (cl4 <= 8 and 3 * b * cl4 <= 2 * sms)) else 8)
     assert info["cols_per_thread"] == (4 if m <= 128 else 8)
     out, err = proc.step(iters)
     assert proc.core.patch_info()["launches"] == 1 and proc.core.info()["launches"] < 12
@@ -183,7 +187,8 @@ def test_persistent_kernel_is_not_used_when_a_tile_shape_is_requested():
 
 
 def test_persistent_kernel_policy():
-    """Used by itself for batches of at least 4 small patches; one small image stays on the tiled kernel."""
+    """Used by itself for batches, for single images up to 128 rows, and for taller single images whose pixels are
+    all unknowns (the select-free stream); a taller single image with an arbitrary mask stays on the tiled kernel."""
     import fpie_b200
     from fpie_b200 import synth
 
@@ -191,9 +196,18 @@ def test_persistent_kernel_policy():
     proc = fpie_b200.BatchGridProcessor("max", "b200")
     proc.reset(src, mask, tgt)
     assert proc.core.patch_info()["usable"]
-    proc.reset(src[:3], mask[:3], tgt[:3])
-    assert not proc.core.patch_info()["usable"]
+    proc.reset(src[:1], mask[:1], tgt[:1])
+    assert proc.core.patch_info()["usable"]
     one = fpie_b200.GridProcessor("max", "b200")
     one.reset(*synth.make_problem("circle", 128, 128, seed=1), (0, 0), (0, 0))
     one.step(64)
-    assert not one.core.patch_info()["usable"] and one.core.patch_info()["launches"] == 0
+    assert one.core.patch_info()["usable"] and one.core.patch_info()["launches"] == 1
+    one.reset(*synth.make_problem("circle", 200, 200, seed=1), (0, 0), (0, 0))
+    one.step(64)
+    assert not one.core.patch_info()["usable"] and one.core.patch_info()["launches"] == 1
+    one.reset(*synth.make_problem("square", 256, 256, seed=1), (0, 0), (0, 0))
+    info = one.core.patch_info()
+    assert info["usable"] and (info["rows_per_thread"], info["cluster"]) == (4, 8)
+    one.reset(*synth.make_problem("square", 300, 256, seed=1), (0, 0), (0, 0))
+    info = one.core.patch_info()
+    assert info["usable"] and (info["rows_per_thread"], info["cluster"]) == (8, 5)  # (more than 8 CTAs of 32 rows)

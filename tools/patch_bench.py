@@ -23,7 +23,10 @@ for b in [int(v) for v in args.batches.split(",")]:
     for mode in args.modes.split(","):
         os.environ.pop("FPIE_B200_PATCH", None); os.environ.pop("FPIE_B200_PATCH_ROWS", None)
         if mode == "off": os.environ["FPIE_B200_PATCH"] = "0"
-        else: os.environ["FPIE_B200_PATCH_ROWS"] = mode
+        elif mode.startswith("force"):  # also for fewer items than the policy wants (single images)
+            os.environ["FPIE_B200_PATCH"] = "2"
+            if mode[5:]: os.environ["FPIE_B200_PATCH_ROWS"] = mode[5:]
+        elif mode != "auto": os.environ["FPIE_B200_PATCH_ROWS"] = mode
         proc = fpie_b200.BatchGridProcessor("src", "b200")
         proc.reset(src, mask, tgt)
         core = proc.core
