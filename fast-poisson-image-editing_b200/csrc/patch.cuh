@@ -160,19 +160,6 @@ struct PatchSmem {
   uint64_t bar[2];
 };
 
-// a predicated st.async (see st_async_cluster4): warps that have no neighbour CTA in that direction issue it with a
-// false predicate instead of branching around it
-__device__ __forceinline__ void st_async_cluster4_if(uint32_t addr, float4 v, uint32_t remote_bar, uint32_t on) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.u32 p, %6, 0;\n"
-      "@p st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];\n"
-      "}\n" ::"r"(addr),
-      "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(remote_bar), "r"(on)
-      : "memory");
-}
-
 // FRAME: every pixel of every patch is an unknown except the 1-pixel frame (the full-square masks of
 // config 5's throughput run and of any whole-image blend): the interior rows of a strip run a select-free
 // stream with two thread-constant column predicates; the strip's first / last row -- which may be the patch's
@@ -181,8 +168,8 @@ __device__ __forceinline__ void st_async_cluster4_if(uint32_t addr, float4 v, ui
 //
 // The sweep loop is branch-free apart from the barrier spin: where a strip's neighbour rows come from (the
 // next warp's slot, the slot a neighbour CTA writes, or -- at the patch's edge, where the row is never used -- the
-// warp's own slot) is an address computed once, the rows for the neighbour CTAs leave through predicated
-// st.async, and the loop is unrolled twice so that the register rotation at its back edge is paid every other
+// warp's own slot) is an address computed once, the rows for the neighbour CTAs leave behind ONE
+// warp-uniform branch, and the loop is unrolled twice so that the register rotation at its back edge is paid every other
 // sweep.  (Before: 399 issued instructions per warp and sweep for 256 FFMA, 8 % of the samples resolving
 // branches, two-way bank conflicts on every mailbox access -- profiles/r02_patch_ncu_full_summary.txt.)
 template <int R, int NW, int CPT, bool FRAME>
@@ -209,15 +196,15 @@ grid_patch_kernel(PlaneGeom g, BatchMap bm, float *__restrict__ x, const float *
   const uint32_t mail_base = smem_u32(&sm.mail[0][0][0][0]);
   const uint32_t bar_base = smem_u32(&sm.bar[0]);
   // my top row goes to the CTA above (its slot 2NW+1), my bottom row to the CTA below (slot 2NW)
-  const uint32_t send_up = (w == 0 && has_up) ? 1u : 0u, send_dn = (w == NW - 1 && has_dn) ? 1u : 0u;
-  uint32_t rem_mail_up = 0, rem_bar_up = 0, rem_mail_dn = 0, rem_bar_dn = 0;
+  // (warp 0 sends up, warp NW - 1 down: never both, NW >= 2)
+  const bool send_up = (w == 0 && has_up), send_dn = (w == NW - 1 && has_dn);
+  uint32_t rem_mail = 0, rem_bar = 0;
   if (send_up) {
-    rem_mail_up = map_to_cta(mail_base + (2 * NW + 1) * SLOT_BYTES + lane * 16, crank - 1);
-    rem_bar_up = map_to_cta(bar_base, crank - 1);
-  }
-  if (send_dn) {
-    rem_mail_dn = map_to_cta(mail_base + (2 * NW) * SLOT_BYTES + lane * 16, crank + 1);
-    rem_bar_dn = map_to_cta(bar_base, crank + 1);
+    rem_mail = map_to_cta(mail_base + (2 * NW + 1) * SLOT_BYTES + lane * 16, crank - 1);
+    rem_bar = map_to_cta(bar_base, crank - 1);
+  } else if (send_dn) {
+    rem_mail = map_to_cta(mail_base + (2 * NW) * SLOT_BYTES + lane * 16, crank + 1);
+    rem_bar = map_to_cta(bar_base, crank + 1);
   }
   // where the rows above / below this warp's strip are read from (byte offsets inside a parity block)
   const int up_slot = (w > 0) ? NW + w - 1 : (has_up ? 2 * NW : w);
@@ -225,7 +212,7 @@ grid_patch_kernel(PlaneGeom g, BatchMap bm, float *__restrict__ x, const float *
   const uint32_t my_top = mail_base + w * SLOT_BYTES + lane * 16, my_bot = mail_base + (NW + w) * SLOT_BYTES + lane * 16;
   const uint32_t up_src = mail_base + up_slot * SLOT_BYTES + lane * 16, dn_src = mail_base + dn_slot * SLOT_BYTES + lane * 16;
   const uint32_t remote_bytes = ((has_up ? 1u : 0u) + (has_dn ? 1u : 0u)) * SLOT_BYTES;
-  const bool arms = (w == 0 && remote_bytes != 0u);
+  const uint32_t arm_bytes = (w == 0) ? remote_bytes : 0u;
   auto sts4 = [](uint32_t addr, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
   };
@@ -283,19 +270,26 @@ grid_patch_kernel(PlaneGeom g, BatchMap bm, float *__restrict__ x, const float *
       for (int q = 0; q < Q; ++q) {
         sts4(my_top + poff + q * 512, xr[0].v[q]);
         sts4(my_bot + poff + q * 512, xr[R - 1].v[q]);
-        // boundary warps: the row also goes to the neighbour CTA (data + notification in one message)
-        st_async_cluster4_if(rem_mail_up + poff + q * 512, xr[0].v[q], rem_bar_up + parity * 8, send_up);
-        st_async_cluster4_if(rem_mail_dn + poff + q * 512, xr[R - 1].v[q], rem_bar_dn + parity * 8, send_dn);
+      }
+      if (rem_bar) {  // boundary warps (one warp-uniform branch per sweep): the row also goes to the neighbour CTA
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          const float4 a = xr[0].v[q], b = xr[R - 1].v[q];
+          const float4 e = make_float4(send_up ? a.x : b.x, send_up ? a.y : b.y, send_up ? a.z : b.z, send_up ? a.w : b.w);
+          st_async_cluster4(rem_mail + poff + q * 512, e, rem_bar + parity * 8);
+        }
       }
       __syncwarp();
-      if (lane == 0) {
-        // warp 0 also announces the bytes the neighbour CTAs store into this CTA's mailbox in this phase
-        if (arms)
-          mbar_expect_tx(bar, remote_bytes);
-        else
-          mbar_arrive(bar);
-      }
-      __syncwarp();
+      // one arrival per warp (lane 0, a predicated instruction rather than a branch); warp 0's arrival also
+      // announces the bytes the neighbour CTAs store into this CTA's mailbox in this phase (0 bytes = a plain arrive)
+      asm volatile(
+          "{\n"
+          ".reg .pred p;\n"
+          "setp.eq.u32 p, %2, 0;\n"
+          "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n"
+          "}\n" ::"r"(smem_u32(bar)),
+          "r"(arm_bytes), "r"((uint32_t)lane)
+          : "memory");
       float lf[R], rt[R];
 #pragma unroll
       for (int i = 0; i < R; ++i) {
@@ -304,20 +298,28 @@ grid_patch_kernel(PlaneGeom g, BatchMap bm, float *__restrict__ x, const float *
       }
       const RowVec<CPT> first_old = xr[1];
       RowVec<CPT> prev = xr[0];
+      RowVec<CPT> up, dn;
+      // tall strips pull the neighbours' rows a few interior rows before they are needed -- the barrier has
+      // normally completed by then and the shared-memory latency hides behind the remaining rows (+2 % at 8 rows
+      // per thread); with 4 rows per thread the barrier has NOT completed that early (-9 %): those wait last
+      constexpr int PULL_ROW = (R >= 8) ? R - 4 : R - 1;
+      auto pull = [&]() {
+        mbar_wait(bar, (mphase >> parity) & 1u);
+        mphase ^= 1u << parity;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          up.v[q] = lds4(up_src + poff + q * 512);
+          dn.v[q] = lds4(dn_src + poff + q * 512);
+        }
+      };
 #pragma unroll
       for (int i = 1; i < R - 1; ++i) {
+        if (i == PULL_ROW) pull();
         const RowVec<CPT> cur = xr[i];
         patch_row_update_lr<CPT, FRAME>(xr[i], hr[i], prev, xr[i + 1], FRAME ? fsel : sel[i], lf[i], rt[i]);
         prev = cur;
       }
-      mbar_wait(bar, (mphase >> parity) & 1u);
-      mphase ^= 1u << parity;
-      RowVec<CPT> up, dn;
-#pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        up.v[q] = lds4(up_src + poff + q * 512);
-        dn.v[q] = lds4(dn_src + poff + q * 512);
-      }
+      if (PULL_ROW >= R - 1) pull();
       // (at the patch's first / last row `up` / `dn` is the strip's own row: never used, those rows have no unknowns)
       if (FRAME) {
         // the patch's first / last row (a warp-uniform condition) is never updated; every other strip edge is an
