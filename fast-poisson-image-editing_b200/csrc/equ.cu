@@ -284,14 +284,17 @@ equ_sweep_d16_kernel(long long N, long long pitch, const uint32_t *__restrict__ 
 // same ~260 us on config 3 as the 8-byte and the 16-byte table kernels although it moves a third less: ncu shows no
 // saturated unit (DRAM 72 %, L2 39 %, L1 wavefronts 74 % -- and halving those with 128-bit gathers made it slower),
 // only warps waiting on memory: a thread's gathers cannot start before its table entry has arrived, two dependent
-// trips to DRAM per unknown.  Here a CTA strides over the system and a thread fetches the table entry and B of its
+// trips to DRAM per unknown.  Here a CTA strides over the system and a thread fetches the table entry of its
 // NEXT four unknowns before it gathers for the current four, so the two trips of consecutive chunks overlap:
 // 262 -> 235 us per sweep on config 3 (135 -> 150 Gupd/s, 5.0 TB/s of DRAM traffic).  Measured around it: fetching
 // two chunks ahead helps at equal occupancy (124 -> 142 Gupd/s at three CTAs per SM) but needs 80 registers, and
 // four CTAs per SM with one chunk ahead is faster (150); prefetching the centre vectors as well: 114; half the
 // occupancy: 117 -- the kernel is bound by memory latency x resident warps, under the board's power cap
 // (SM clock 1.6 GHz in these runs).
-template <bool BH>
+// D = how many chunks ahead the TABLE entry is fetched (FPIE_B200_D16_DEPTH; 1 is the default: 155 Gupd/s on config 3,
+// two ahead 151).  Only the table entry gates the gathers; B is needed when the sums are formed and is loaded with
+// the chunk's own centre vectors and gathers (prefetching it as well measured the same and costs 6 registers).
+template <bool BH, int D>
 __global__ void __launch_bounds__(256, BH ? 4 : 3)
 equ_sweep_d16p_kernel(long long N, long long pitch, const uint32_t *__restrict__ D16, const float *__restrict__ B,
                       const __half *__restrict__ B16, const float *__restrict__ xin, float *__restrict__ xout) {
@@ -299,25 +302,27 @@ equ_sweep_d16p_kernel(long long N, long long pitch, const uint32_t *__restrict__
   long long i0 = 4 * (blockIdx.x * (long long)blockDim.x + threadIdx.x);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // (see equ_sweep_lr_kernel)
   if (i0 >= N) return;
-  uint4 tv, tvn = make_uint4(0u, 0u, 0u, 0u);
-  uint2 bh[3], bhn[3];
-  float4 bf[3], bfn[3];
-  auto fetch = [&](long long at, uint4 &t4, uint2 (&h)[3], float4 (&f)[3]) {
-    t4 = *reinterpret_cast<const uint4 *>(D16 + at);  // (the table is zero-padded to the pitch)
+  uint4 tq[D + 1];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    tq[d] = make_uint4(0u, 0u, 0u, 0u);
+    if (i0 + d * stride < N) tq[d] = *reinterpret_cast<const uint4 *>(D16 + i0 + d * stride);  // (zero-padded to the pitch)
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  for (; i0 < N; i0 += stride) {
+    const long long inext = i0 + D * stride;
+    tq[D] = make_uint4(0u, 0u, 0u, 0u);
+    if (inext < N) tq[D] = *reinterpret_cast<const uint4 *>(D16 + inext);
+    uint2 bh[3];
+    float4 bf[3];
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
       if (BH)
-        h[ch] = *reinterpret_cast<const uint2 *>(B16 + ch * pitch + at);
+        bh[ch] = *reinterpret_cast<const uint2 *>(B16 + ch * pitch + i0);
       else
-        f[ch] = ld4(B + ch * pitch + at);
+        bf[ch] = ld4(B + ch * pitch + i0);
     }
-  };
-  fetch(i0, tv, bh, bf);
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  for (; i0 < N; i0 += stride) {
-    const long long inext = i0 + stride;
-    if (inext < N) fetch(inext, tvn, bhn, bfn);
-    const uint32_t t[4] = {tv.x, tv.y, tv.z, tv.w};
+    const uint32_t t[4] = {tq[0].x, tq[0].y, tq[0].z, tq[0].w};
     int up[4], dn[4];  // (ids are int32: EquSolver::reset requires N < 2^31)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -358,9 +363,8 @@ equ_sweep_d16p_kernel(long long N, long long pitch, const uint32_t *__restrict__
           if (i0 + j < N) xout[ch * pitch + i0 + j] = o[j];
       }
     }
-    tv = tvn;
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) bh[ch] = bhn[ch], bf[ch] = bfn[ch];
+    for (int d = 0; d < D; ++d) tq[d] = tq[d + 1];
   }
 }
 
@@ -895,7 +899,9 @@ void EquSolver::sweeps_async(int iters) {
       const __half *b16 = b16_.ptr;
       cfg.blockDim = dim3(256);
       cfg.gridDim = dim3((unsigned)blocks_for((N_ + 3) / 4, 256));
-      auto kern = d16_pipe_ ? (b16_ok_ ? equ_sweep_d16p_kernel<true> : equ_sweep_d16p_kernel<false>)
+      static const int depth = getenv("FPIE_B200_D16_DEPTH") ? atoi(getenv("FPIE_B200_D16_DEPTH")) : 1;
+      auto kern = d16_pipe_ ? (b16_ok_ ? (depth == 2 ? equ_sweep_d16p_kernel<true, 2> : equ_sweep_d16p_kernel<true, 1>)
+                                       : (depth == 2 ? equ_sweep_d16p_kernel<false, 2> : equ_sweep_d16p_kernel<false, 1>))
                             : (b16_ok_ ? equ_sweep_d16_kernel<true> : equ_sweep_d16_kernel<false>);
       if (d16_pipe_)  // persistent: d16_ctas_per_sm_ CTAs per SM stride over the system
         cfg.gridDim = dim3((unsigned)std::min<long long>(cfg.gridDim.x, (long long)sm_count_ * std::min(d16_ctas_per_sm_, b16_ok_ ? 4 : 3)));
