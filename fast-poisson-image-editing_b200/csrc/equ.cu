@@ -621,6 +621,7 @@ EquSolver::~EquSolver() {
   cudaGetDevice(&prev);
   cudaSetDevice(device_);
   drop_graphs();
+  upload_.destroy_stream();
   if (cap_stream_) cudaStreamDestroy(cap_stream_);
   if (host_err_) cudaFreeHost(host_err_);
   if (host_flag_) cudaFreeHost(host_flag_);

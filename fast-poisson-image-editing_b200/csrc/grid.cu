@@ -610,12 +610,15 @@ grid_to_u8_kernel(PlaneGeom g, BatchMap bm, const float *__restrict__ x, uint8_t
 // consecutive plane columns of one crop row -- mask word by ballot, state from
 // the target crop, quarter-scaled mixed gradient on masked pixels.
 __global__ void __launch_bounds__(256)
-grid_build_kernel(PlaneGeom g, BlendImages b, int equ_form, uint32_t *__restrict__ bits, float *__restrict__ x0,
-                  float *__restrict__ x1, float *__restrict__ hq, unsigned long long *__restrict__ count) {
+grid_build_kernel(PlaneGeom g, BlendImages b, int equ_form, int row_lo, int row_hi, uint32_t *__restrict__ bits,
+                  float *__restrict__ x0, float *__restrict__ x1, float *__restrict__ hq,
+                  unsigned long long *__restrict__ count) {
+  // crop rows [row_lo, row_hi): the whole grid, or the rows whose source / target rows have arrived (the upload
+  // comes in row chunks and the build of a chunk runs beside the copy of the next)
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  if (warp >= (long long)g.n * g.wpitch) return;
-  const int r = (int)(warp / g.wpitch);
+  if (warp >= (long long)(row_hi - row_lo) * g.wpitch) return;
+  const int r = row_lo + (int)(warp / g.wpitch);
   const int pcol = (int)(warp % g.wpitch) * 32 + lane;
   const int c = pcol - g.padc;
   BlendImages pb;
@@ -762,6 +765,7 @@ GridSolver::~GridSolver() {
   cudaGetDevice(&prev);
   cudaSetDevice(device_);
   drop_graphs();
+  upload_.destroy_stream();
   if (cap_stream_) cudaStreamDestroy(cap_stream_);
   if (host_err_) cudaFreeHost(host_err_);
   if (prev >= 0 && prev != device_) cudaSetDevice(prev);
@@ -902,7 +906,7 @@ void GridSolver::reset_from_images(const uint8_t *src, int sh, int sw, const uin
   DeviceGuard guard(device_);
   ready_ = false;
   BlendUpload &up = upload_;  // device copies of the images are kept between resets (no malloc / free per call)
-  up.upload(stream_, src, sh, sw, mask, mh, mw, mc, tgt, th, tw, h0, w0, h1, w1, grad_mode, crop);
+  up.upload(stream_, src, sh, sw, mask, mh, mw, mc, tgt, th, tw, h0, w0, h1, w1, grad_mode, crop, &chunks_);
   batch_ = BatchMap{0, 0, 0, 0};
   build_from_upload();
   const BlendImages &b = up.images();
@@ -927,6 +931,7 @@ void GridSolver::reset_batch(const uint8_t *src, const uint8_t *mask, const uint
   int bcols = 1;
   while (bcols * pw < 4096 && bcols < batch) bcols *= 2;
   upload_.upload_batch(stream_, src, mask, tgt, batch, ph, pw, mc, grad_mode, bcols);
+  chunks_.count = 0;
   batch_ = BatchMap{batch, ph, pw, bcols};
   batch_err_.resize((size_t)batch * 3);
   build_from_upload();
@@ -995,12 +1000,29 @@ void GridSolver::build_from_upload() {
   zeroed_ptr_[3] = (float *)bits_.ptr;
   zeroed_batch_ = batch_.batch > 0;
   CUDA_CHECK(cudaMemsetAsync(err_.ptr, 0, err_.bytes(), stream_));
-  const long long warps = (long long)g.n * g.wpitch;
-  grid_build_kernel<<<blocks_for(warps * 32, 256), 256, 0, stream_>>>(
-      g, b, equ_form_ ? 1 : 0, bits_.ptr, x_[0].ptr, x_[1].ptr, hq_.ptr,
-      reinterpret_cast<unsigned long long *>(err_.ptr + 3));
-  CUDA_CHECK(cudaGetLastError());
-  stats_.launches += 2;
+  auto build_rows = [&](int lo, int hi) {
+    if (hi <= lo) return;
+    const long long warps = (long long)(hi - lo) * g.wpitch;
+    grid_build_kernel<<<blocks_for(warps * 32, 256), 256, 0, stream_>>>(
+        g, b, equ_form_ ? 1 : 0, lo, hi, bits_.ptr, x_[0].ptr, x_[1].ptr, hq_.ptr,
+        reinterpret_cast<unsigned long long *>(err_.ptr + 3));
+    CUDA_CHECK(cudaGetLastError());
+    stats_.launches += 1;
+  };
+  if (chunks_.count > 0) {
+    // a crop row reads the source / target rows above and below it: the build lags the copies by one row
+    int lo = 0;
+    for (int k = 0; k < chunks_.count; ++k) {
+      const int hi = (k + 1 == chunks_.count) ? g.n : std::max(chunks_.row_hi[k] - 1, lo);
+      CUDA_CHECK(cudaStreamWaitEvent(stream_, chunks_.ev[k], 0));
+      build_rows(lo, hi);
+      lo = hi;
+    }
+    chunks_.count = 0;
+  } else {
+    build_rows(0, g.n);
+  }
+  stats_.launches += 1;
   after_state_loaded();
 }
 

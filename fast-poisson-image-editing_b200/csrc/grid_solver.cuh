@@ -144,6 +144,7 @@ class GridSolver {
   DeviceBuffer<uint32_t> bits_;
   DeviceBuffer<float> stage_;
   BlendUpload upload_;
+  UploadChunks chunks_;  // row chunks of the last crop-mode upload (consumed by build_from_upload)
   BatchMap batch_{0, 0, 0, 0};
   DeviceBuffer<double> batch_err_;
   DeviceBuffer<int32_t> mask_stage_;

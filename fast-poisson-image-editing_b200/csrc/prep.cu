@@ -57,6 +57,20 @@ void BlendUpload::release() {
   tgt_.release();
 }
 
+// (called by the owning solver's destructor while its device is current; idempotent)
+void BlendUpload::destroy_stream() {
+  if (copy_stream_) cudaStreamDestroy(copy_stream_);
+  if (start_ev_) cudaEventDestroy(start_ev_);
+  for (auto &e : chunk_ev_) {
+    if (e) cudaEventDestroy(e);
+    e = nullptr;
+  }
+  copy_stream_ = nullptr;
+  start_ev_ = nullptr;
+}
+
+BlendUpload::~BlendUpload() { destroy_stream(); }
+
 void BlendUpload::upload_batch(cudaStream_t stream, const uint8_t *src, const uint8_t *mask, const uint8_t *tgt,
                                int batch, int ph, int pw, int mc, int mode, int bcols) {
   FPIE_REQUIRE(src && mask && tgt, "reset_batch: null image");
@@ -88,7 +102,7 @@ void BlendUpload::upload_batch(cudaStream_t stream, const uint8_t *src, const ui
 
 void BlendUpload::upload(cudaStream_t stream, const uint8_t *src, int sh, int sw, const uint8_t *mask, int mh, int mw,
                          int mc, const uint8_t *tgt, int th, int tw, int h0, int w0, int h1, int w1, int mode,
-                         bool crop) {
+                         bool crop, UploadChunks *chunks) {
   FPIE_REQUIRE(src && mask && tgt, "reset_from_images: null image");
   FPIE_REQUIRE(sh > 0 && sw > 0 && mh > 0 && mw > 0 && th > 0 && tw > 0, "reset_from_images: empty image");
   FPIE_REQUIRE(mc >= 1 && mc <= 16, "reset_from_images: mask must have 1..16 channels");
@@ -98,9 +112,8 @@ void BlendUpload::upload(cudaStream_t stream, const uint8_t *src, int sh, int sw
   mask_.resize(mbytes);
   tgt_.resize(tbytes);
   box_.resize(4);
-  CUDA_CHECK(cudaMemcpyAsync(src_.ptr, src, sbytes, cudaMemcpyHostToDevice, stream));
+  if (chunks) chunks->count = 0;
   CUDA_CHECK(cudaMemcpyAsync(mask_.ptr, mask, mbytes, cudaMemcpyHostToDevice, stream));
-  CUDA_CHECK(cudaMemcpyAsync(tgt_.ptr, tgt, tbytes, cudaMemcpyHostToDevice, stream));
   const int init[4] = {INT_MAX, INT_MIN, INT_MAX, INT_MIN};
   CUDA_CHECK(cudaMemcpyAsync(box_.ptr, init, sizeof(init), cudaMemcpyHostToDevice, stream));
 
@@ -121,6 +134,8 @@ void BlendUpload::upload(cudaStream_t stream, const uint8_t *src, int sh, int sw
     b.m = mw;
     FPIE_REQUIRE(h0 >= 0 && w0 >= 0 && h0 + mh <= sh && w0 + mw <= sw, "reset: the slab falls outside the source image");
     FPIE_REQUIRE(h1 >= 0 && w1 >= 0 && h1 + mh <= th && w1 + mw <= tw, "reset: the slab falls outside the target image");
+    CUDA_CHECK(cudaMemcpyAsync(src_.ptr, src, sbytes, cudaMemcpyHostToDevice, stream));
+    CUDA_CHECK(cudaMemcpyAsync(tgt_.ptr, tgt, tbytes, cudaMemcpyHostToDevice, stream));
     img_ = b;
     return;
   }
@@ -142,6 +157,39 @@ void BlendUpload::upload(cudaStream_t stream, const uint8_t *src, int sh, int sw
                "reset: the mask bounding box falls outside the source image");
   FPIE_REQUIRE(h1 + b.x0 >= 0 && w1 + b.y0 >= 0 && h1 + b.x0 + b.n <= th && w1 + b.y0 + b.m <= tw,
                "reset: the mask bounding box falls outside the target image");
+  // Only the crop's rows of the source and the target are read on the device (every gradient term of a masked
+  // pixel stays inside the crop: its frame is unmasked): copy those rows, in chunks, on the uploader's own stream.
+  if (!copy_stream_) {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&start_ev_, cudaEventDisableTiming));
+    for (auto &e : chunk_ev_) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  // (whatever still reads the previous images was enqueued on `stream`)
+  CUDA_CHECK(cudaEventRecord(start_ev_, stream));
+  CUDA_CHECK(cudaStreamWaitEvent(copy_stream_, start_ev_, 0));
+  const size_t srow = (size_t)sw * 3, trow = (size_t)tw * 3;
+  const size_t crop_bytes = (size_t)b.n * (srow + trow);
+  const int parts = (int)std::min<size_t>(UploadChunks::kMax, std::max<size_t>(1, crop_bytes / (12u << 20)));
+  const uint8_t *s0 = src + (size_t)(h0 + b.x0) * srow, *t0 = tgt + (size_t)(h1 + b.x0) * trow;
+  uint8_t *ds0 = src_.ptr + (size_t)(h0 + b.x0) * srow, *dt0 = tgt_.ptr + (size_t)(h1 + b.x0) * trow;
+  int done = 0;
+  for (int k = 0; k < parts; ++k) {
+    const int hi = (int)((long long)b.n * (k + 1) / parts);
+    if (hi > done) {
+      CUDA_CHECK(cudaMemcpyAsync(ds0 + done * srow, s0 + done * srow, (size_t)(hi - done) * srow, cudaMemcpyHostToDevice, copy_stream_));
+      CUDA_CHECK(cudaMemcpyAsync(dt0 + done * trow, t0 + done * trow, (size_t)(hi - done) * trow, cudaMemcpyHostToDevice, copy_stream_));
+    }
+    CUDA_CHECK(cudaEventRecord(chunk_ev_[k], copy_stream_));
+    if (chunks) {
+      chunks->row_hi[k] = hi;
+      chunks->ev[k] = chunk_ev_[k];
+    }
+    done = hi;
+  }
+  if (chunks)
+    chunks->count = parts;
+  else
+    CUDA_CHECK(cudaStreamWaitEvent(stream, chunk_ev_[parts - 1], 0));
   img_ = b;
 }
 

@@ -39,20 +39,38 @@ struct CropBox {
 // Upload the images (host -> device buffers owned by the caller), find the
 // bounding box of the canonical mask and validate it against src / tgt.
 // Throws fpie::Error for an empty mask or a box that leaves an image.
+// Row chunks of a crop-mode upload: crop rows [0, row_hi[k]) of the source and the target are on the device once
+// ev[k] has completed (the copies run on the uploader's own stream, beside whatever the caller enqueues).
+struct UploadChunks {
+  static constexpr int kMax = 8;
+  int count = 0;
+  int row_hi[kMax] = {};
+  cudaEvent_t ev[kMax] = {};
+};
+
 class BlendUpload {
  public:
+  ~BlendUpload();
+  // The mask goes first: its bounding box decides which rows of the source and the target are needed at all
+  // (only those are copied), and the caller learns the crop geometry while they are still on their way.  With
+  // `chunks` the caller gets one event per row chunk and orders its own work behind them; without, `stream` itself
+  // waits for the last copy.
   void upload(cudaStream_t stream, const uint8_t *src, int sh, int sw, const uint8_t *mask, int mh, int mw, int mc,
-              const uint8_t *tgt, int th, int tw, int h0, int w0, int h1, int w1, int mode, bool crop = true);
+              const uint8_t *tgt, int th, int tw, int h0, int w0, int h1, int w1, int mode, bool crop = true,
+              UploadChunks *chunks = nullptr);
   // `batch` patches of ph x pw pixels each (src / tgt [batch, ph, pw, 3], mask [batch, ph, pw, mc])
   void upload_batch(cudaStream_t stream, const uint8_t *src, const uint8_t *mask, const uint8_t *tgt, int batch, int ph,
                     int pw, int mc, int mode, int bcols);
   const BlendImages &images() const { return img_; }
   void release();
+  void destroy_stream();
 
  private:
   DeviceBuffer<uint8_t> src_, mask_, tgt_;
   DeviceBuffer<int> box_;
   BlendImages img_{};
+  cudaStream_t copy_stream_ = nullptr;  // created on first use, on the device that is current then
+  cudaEvent_t start_ev_ = nullptr, chunk_ev_[UploadChunks::kMax] = {};
 };
 
 #ifdef __CUDACC__

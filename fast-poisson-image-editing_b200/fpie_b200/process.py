@@ -41,12 +41,13 @@ class BaseProcessor:
         self.core = core
         self.rank = 0
         self.root = True
-        self.tgt = None
+        self._canvas_stale = False
+        self._tgt = None
         self.box = None
         self._canvas_pool = []
 
     def _require_reset(self) -> None:
-        if self.tgt is None or self.box is None:  # the same error the core raises (GridSolver::require_ready)
+        if self._tgt is None or self.box is None:  # the same error the core raises (GridSolver::require_ready)
             raise RuntimeError(f"{type(self).__name__}: step called before reset")
 
     def sync(self) -> None:
@@ -85,23 +86,62 @@ class BaseProcessor:
                 canvas = np.empty(tgt.shape, np.uint8)
             self._canvas_pool.append(canvas)
             del self._canvas_pool[:-3]  # (a dropped canvas lives on for as long as its holder keeps it)
-        rows = tgt.shape[0]
+        rows, cols = tgt.shape[0], tgt.shape[1]
         parts = 4 if tgt.size >= (8 << 20) else 1  # large images: fault the fresh pages in from several threads
         bounds = [rows * i // parts for i in range(parts + 1)]
+        block = max(1, (1 << 20) // max(1, tgt.strides[0]))  # rows per copy call: about 1 MB
+        known = [None]  # the blend's bounding box (x0, x1, y0, y1) in the target, once the device has found it
 
         def copy(lo, hi):
-            np.copyto(canvas[lo:hi], tgt[lo:hi], casting="unsafe")
+            # The device returns the blended crop into canvas[x0:x1, y0:y1] (at zero sweeps: the target's own pixels),
+            # so only what lies OUTSIDE the box has to come from `tgt`.  The box is not known when the workers start:
+            # they copy whole rows until it is, and skip its inside from then on -- a 4096^2 target whose box is the
+            # whole image costs nothing beyond the device-side reset instead of outlasting it by a millisecond.
+            r = lo
+            while r < hi:
+                e = min(hi, r + block)
+                box = known[0]
+                a, b = (max(r, box[0]), min(e, box[1])) if box else (e, e)
+                if a >= b:
+                    np.copyto(canvas[r:e], tgt[r:e], casting="unsafe")
+                else:
+                    if r < a:
+                        np.copyto(canvas[r:a], tgt[r:a], casting="unsafe")
+                    if b < e:
+                        np.copyto(canvas[b:e], tgt[b:e], casting="unsafe")
+                    if box[2] > 0:
+                        np.copyto(canvas[a:b, : box[2]], tgt[a:b, : box[2]], casting="unsafe")
+                    if box[3] < cols:
+                        np.copyto(canvas[a:b, box[3] :], tgt[a:b, box[3] :], casting="unsafe")
+                r = e
 
         workers = [threading.Thread(target=copy, args=(bounds[i], bounds[i + 1])) for i in range(parts)]
         for wk in workers:
             wk.start()
         try:
             result = device_reset()
+            known[0] = tuple(int(v) for v in result[1])
         finally:
-            for wk in workers:
+            for wk in workers:  # (every read of the caller's `tgt` has completed when reset returns)
                 wk.join()
-        self.tgt = canvas
+        self._tgt = canvas
+        self._canvas_stale = True  # the inside of the box is still to come from the device: `tgt` / `step` fetch it
         return result
+
+    def _fetch_into_canvas(self, iteration: int):
+        raise NotImplementedError
+
+    @property
+    def tgt(self):
+        """The Processor's private copy of the target (process.py:268 / 384), holding the blend after ``step``."""
+        if self._canvas_stale and self._tgt is not None and self.box is not None:
+            self._fetch_into_canvas(0)
+        return self._tgt
+
+    @tgt.setter
+    def tgt(self, value) -> None:
+        self._tgt = value
+        self._canvas_stale = False
 
     @staticmethod
     def _check_images(src, mask, tgt):
@@ -131,9 +171,13 @@ class EquProcessor(BaseProcessor):
         # process.py:278 `self.tgt[self.tgt_index] = x[1:]`: the device scatters the K solved pixels into
         # its copy of the crop, the device-to-host copy lands it in self.tgt[x0:x1, y0:y1]
         self._require_reset()
+        return self._tgt, self._fetch_into_canvas(iteration)
+
+    def _fetch_into_canvas(self, iteration: int):
         x0, _, y0, _ = self.box
-        err = self.core.step_paste_into(iteration, self.tgt, x0, y0)
-        return self.tgt, err
+        err = self.core.step_paste_into(iteration, self._tgt, x0, y0)
+        self._canvas_stale = False
+        return err
 
 
 class GridProcessor(BaseProcessor):
@@ -156,8 +200,12 @@ class GridProcessor(BaseProcessor):
     def step(self, iteration: int):
         # process.py:393 `self.tgt[x0:x1, y0:y1] = tgt`, done by the device-to-host copy itself
         self._require_reset()
-        err = self.core.step_into(iteration, self.tgt, self.x0, self.y0)
-        return self.tgt, err
+        return self._tgt, self._fetch_into_canvas(iteration)
+
+    def _fetch_into_canvas(self, iteration: int):
+        err = self.core.step_into(iteration, self._tgt, self.x0, self.y0)
+        self._canvas_stale = False
+        return err
 
 
 class BatchGridProcessor(BaseProcessor):

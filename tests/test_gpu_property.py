@@ -144,3 +144,40 @@ def test_solve_stops_where_the_oracle_stops(solver_kind):
     assert proc.solve(0, 0.0, 25)[2] == 0
     with pytest.raises(RuntimeError):
         proc.core.solve(10, 1.0, 0)
+
+
+@pytest.mark.parametrize("kind", ["grid", "equ"])
+@pytest.mark.parametrize("where", ["small box in a large target", "box = the whole target"])
+def test_canvas_is_the_target_outside_the_box_and_the_device_crop_inside(kind, where):
+    """`reset` copies the caller's target only OUTSIDE the blend's bounding box (several threads for a large image,
+    the box unknown when they start); the inside comes from the device.  Whatever the split: `proc.tgt` equals the
+    target before any step (process.py:268 / 384 `self.tgt = tgt.copy()`), the oracle's image after, is the same
+    buffer every time, and the caller's array can be overwritten as soon as `reset` has returned."""
+    import fpie_b200
+    from fpie_b200 import synth
+
+    rng = np.random.default_rng(3)
+    if where.startswith("small"):
+        tgt = rng.integers(0, 256, (2100, 1500, 3), dtype=np.uint8)  # > 8 MB: the threaded copy
+        src = rng.integers(0, 256, (300, 260, 3), dtype=np.uint8)
+        mask = synth.make_mask("circle", 200, 180)
+        on_src, on_tgt = (40, 30), (1234, 777)
+    else:
+        tgt = rng.integers(0, 256, (1800, 1700, 3), dtype=np.uint8)
+        src = rng.integers(0, 256, (1800, 1700, 3), dtype=np.uint8)
+        mask = np.full((1800, 1700), 255, np.uint8)
+        on_src, on_tgt = (0, 0), (0, 0)
+    Proc = fpie_b200.GridProcessor if kind == "grid" else fpie_b200.EquProcessor
+    want = (np_oracle.GridOracle if kind == "grid" else np_oracle.EquOracle)("max")
+    n_want = want.reset(src, mask, tgt, on_src, on_tgt)
+    for round_ in range(2):  # (the second reset recycles the page-locked canvas of the first)
+        proc = Proc("max", "b200") if round_ == 0 else proc
+        mine = tgt.copy()
+        assert proc.reset(src, mask, mine, on_src, on_tgt) == n_want
+        mine[...] = 0  # the caller's buffer is its own again
+        before = proc.tgt
+        np.testing.assert_array_equal(before, tgt)
+        out, _ = proc.step(33)
+        assert out is before and out is proc.tgt
+    want_out, _ = want.step(33)
+    np.testing.assert_array_equal(out, want_out)
