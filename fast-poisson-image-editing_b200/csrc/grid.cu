@@ -751,7 +751,7 @@ GridSolver::GridSolver(int device, cudaStream_t stream, int block_k, int variant
   // FPIE_B200_PATCH_ROWS=4|8 overrides the rows per thread
   const char *patch = getenv("FPIE_B200_PATCH");
   patch_off_ = patch && patch[0] == '0';
-  patch_force_ = patch && patch[0] == '2';  // FPIE_B200_PATCH=2: also for fewer than 12 items (single images)
+  patch_force_ = patch && patch[0] == '2';  // (FPIE_B200_PATCH=2 once forced the kernel for small batches; it is the policy now)
   const char *prow = getenv("FPIE_B200_PATCH_ROWS");
   patch_rows_ = prow ? atoi(prow) : 0;
   if (patch_rows_ != 4 && patch_rows_ != 8) patch_rows_ = 0;
@@ -1501,10 +1501,9 @@ bool GridSolver::patch_shape(int *rows_per_thread, int *cols_per_thread, int *cl
   // image and 0.79 us for three.  So: 4 rows per thread while every item's cluster fits the device at once (two
   // such CTAs per SM), 8 rows per thread -- half the hand-overs per pixel -- for larger batches (512 patches of
   // 256^2: 1336 vs 1123 Gupd/s; the tiled kernel: 809); one full-square 256^2 image: 155 vs 125 Gupd/s, 128^2: 61 vs
-  // 32.  A single image taller than 128 rows with an arbitrary mask (per-pixel selects) stays on the tiled kernel.
+  // 32; with an arbitrary mask (per-pixel selects: tools/single_image_bench.py) a single 160^2 ... 256^2 image still
+  // runs 6 % faster here (0.49 vs 0.52 us per sweep).
   const int items = (single ? 1 : batch_.batch) * 3;
-  const bool all_unknown = stats_.unknowns == (int64_t)(items / 3) * (ph - 2) * (pw - 2);
-  if (!patch_force_ && items < 9 && ph > 128 && !all_unknown) return false;
   const int cpt = pw <= 128 ? 4 : 8;
   int r = patch_rows_;
   if (r == 0) {

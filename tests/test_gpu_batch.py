@@ -187,8 +187,8 @@ def test_persistent_kernel_is_not_used_when_a_tile_shape_is_requested():
 
 
 def test_persistent_kernel_policy():
-    """Used by itself for batches, for single images up to 128 rows, and for taller single images whose pixels are
-    all unknowns (the select-free stream); a taller single image with an arbitrary mask stays on the tiled kernel."""
+    """Used by itself for batches and single images of up to 256 columns and 512 rows (any mask); 4 rows per thread
+    while all clusters are resident at once and a plane needs at most 8 CTAs."""
     import fpie_b200
     from fpie_b200 import synth
 
@@ -204,7 +204,10 @@ def test_persistent_kernel_policy():
     assert one.core.patch_info()["usable"] and one.core.patch_info()["launches"] == 1
     one.reset(*synth.make_problem("circle", 200, 200, seed=1), (0, 0), (0, 0))
     one.step(64)
-    assert not one.core.patch_info()["usable"] and one.core.patch_info()["launches"] == 1
+    assert one.core.patch_info()["usable"] and one.core.patch_info()["launches"] == 2
+    one.reset(*synth.make_problem("holes", 200, 300, seed=1), (0, 0), (0, 0))  # wider than 256 columns: tiled
+    one.step(64)
+    assert not one.core.patch_info()["usable"] and one.core.patch_info()["launches"] == 2
     one.reset(*synth.make_problem("square", 256, 256, seed=1), (0, 0), (0, 0))
     info = one.core.patch_info()
     assert info["usable"] and (info["rows_per_thread"], info["cluster"]) == (4, 8)
