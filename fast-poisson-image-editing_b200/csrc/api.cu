@@ -330,6 +330,14 @@ API int fpie_b200_equ_info(fpie_b200_equ *e, int64_t *unknowns, int64_t *launche
     if (path) *path = e->impl.path();
   });
 }
+API int fpie_b200_grid_on_box(fpie_b200_grid *g, fpie_b200_box_fn cb, void *user) {
+  NEED(g);
+  return guarded([&] { g->impl.set_box_callback(cb, user); });
+}
+API int fpie_b200_equ_on_box(fpie_b200_equ *e, fpie_b200_box_fn cb, void *user) {
+  NEED(e);
+  return guarded([&] { e->impl.set_box_callback(cb, user); });
+}
 API int fpie_b200_equ_set_window(fpie_b200_equ *e, int64_t lo, int64_t hi) {
   NEED(e);
   return guarded([&] { e->impl.set_window(lo, hi); });

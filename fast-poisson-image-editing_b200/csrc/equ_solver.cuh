@@ -26,6 +26,7 @@ class EquSolver {
   void reset_from_images(const uint8_t *src, int sh, int sw, const uint8_t *mask, int mh, int mw, int mc,
                          const uint8_t *tgt, int th, int tw, int h0, int w0, int h1, int w1, int grad_mode,
                          int64_t *out_n, int32_t *out_box4);
+  void set_box_callback(void (*cb)(void *, const int32_t *), void *user) { upload_.set_box_callback(cb, user); }
   void sweeps_async(int iters);
   void finish_async();
   void sync();

@@ -57,6 +57,7 @@ class GridSolver {
   void reset_from_images(const uint8_t *src, int sh, int sw, const uint8_t *mask, int mh, int mw, int mc,
                          const uint8_t *tgt, int th, int tw, int h0, int w0, int h1, int w1, int grad_mode,
                          int64_t *out_n, int32_t *out_box4, bool crop = true);
+  void set_box_callback(void (*cb)(void *, const int32_t *), void *user) { upload_.set_box_callback(cb, user); }
   void reset_batch(const uint8_t *src, const uint8_t *mask, const uint8_t *tgt, int batch, int ph, int pw, int mc,
                    int grad_mode);
   // EquSolver promotion: state = X on masked pixels and 0 elsewhere, gradient = B (see equ.cu)

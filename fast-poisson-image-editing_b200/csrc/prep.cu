@@ -157,6 +157,10 @@ void BlendUpload::upload(cudaStream_t stream, const uint8_t *src, int sh, int sw
                "reset: the mask bounding box falls outside the source image");
   FPIE_REQUIRE(h1 + b.x0 >= 0 && w1 + b.y0 >= 0 && h1 + b.x0 + b.n <= th && w1 + b.y0 + b.m <= tw,
                "reset: the mask bounding box falls outside the target image");
+  if (box_cb_) {
+    const int32_t bx[4] = {h1 + b.x0, h1 + b.x0 + b.n, w1 + b.y0, w1 + b.y0 + b.m};
+    box_cb_(box_user_, bx);
+  }
   // Only the crop's rows of the source and the target are read on the device (every gradient term of a masked
   // pixel stays inside the crop: its frame is unmasked): copy those rows, in chunks, on the uploader's own stream.
   if (!copy_stream_) {

@@ -64,11 +64,19 @@ class BlendUpload {
   const BlendImages &images() const { return img_; }
   void release();
   void destroy_stream();
+  // called (on the calling thread, from inside `upload`) as soon as the blend's bounding box in TARGET coordinates
+  // (x0, x1, y0, y1) is known -- before the source / target rows travel: lets the host prepare its side meanwhile
+  void set_box_callback(void (*cb)(void *, const int32_t *), void *user) {
+    box_cb_ = cb;
+    box_user_ = user;
+  }
 
  private:
   DeviceBuffer<uint8_t> src_, mask_, tgt_;
   DeviceBuffer<int> box_;
   BlendImages img_{};
+  void (*box_cb_)(void *, const int32_t *) = nullptr;
+  void *box_user_ = nullptr;
   cudaStream_t copy_stream_ = nullptr;  // created on first use, on the device that is current then
   cudaEvent_t start_ev_ = nullptr, chunk_ev_[UploadChunks::kMax] = {};
 };

@@ -20,6 +20,8 @@ c_void_p = ctypes.c_void_p
 P = ctypes.POINTER
 i32p, f32p, u8p, i64p, intp = P(ctypes.c_int32), P(ctypes.c_float), P(ctypes.c_uint8), P(c_i64), P(c_int)
 
+BOX_FN = ctypes.CFUNCTYPE(None, c_void_p, P(ctypes.c_int32))  # fpie_b200_box_fn
+
 # name -> (argtypes); every function returns int except the two noted below.
 SIGNATURES = {
     "fpie_b200_abi_version": [],
@@ -79,6 +81,8 @@ SIGNATURES = {
     "fpie_b200_equ_step_paste": [c_void_p, c_int, u8p, f32p],
     "fpie_b200_equ_step_paste_into": [c_void_p, c_int, u8p, c_i64, f32p],
     "fpie_b200_equ_system": [c_void_p, i32p, f32p, f32p],
+    "fpie_b200_grid_on_box": [c_void_p, BOX_FN, c_void_p],
+    "fpie_b200_equ_on_box": [c_void_p, BOX_FN, c_void_p],
     "fpie_b200_equ_set_window": [c_void_p, c_i64, c_i64],
     "fpie_b200_equ_fetch_rows": [c_void_p, c_i64, c_i64, u8p, f32p],
     "fpie_b200_equ_gather_rows": [c_void_p, c_void_p, c_i64, c_void_p],

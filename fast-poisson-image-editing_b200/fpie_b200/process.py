@@ -94,9 +94,8 @@ class BaseProcessor:
 
         def copy(lo, hi):
             # The device returns the blended crop into canvas[x0:x1, y0:y1] (at zero sweeps: the target's own pixels),
-            # so only what lies OUTSIDE the box has to come from `tgt`.  The box is not known when the workers start:
-            # they copy whole rows until it is, and skip its inside from then on -- a 4096^2 target whose box is the
-            # whole image costs nothing beyond the device-side reset instead of outlasting it by a millisecond.
+            # so only what lies OUTSIDE the box has to come from `tgt` -- a 4096^2 target whose box is the whole image
+            # costs nothing beyond the device-side reset instead of outlasting it by a millisecond.
             r = lo
             while r < hi:
                 e = min(hi, r + block)
@@ -115,15 +114,38 @@ class BaseProcessor:
                         np.copyto(canvas[a:b, box[3] :], tgt[a:b, box[3] :], casting="unsafe")
                 r = e
 
-        workers = [threading.Thread(target=copy, args=(bounds[i], bounds[i + 1])) for i in range(parts)]
-        for wk in workers:
-            wk.start()
+        workers = []
+
+        def start(box=None):
+            # Called by the core as soon as the box is known (the mask travels first, the images after it): with the
+            # box covering the whole target there is nothing to copy; otherwise the workers run beside the rest of
+            # the device-side reset.  (Also called with no box by the fallback below.)
+            if workers:
+                return
+            known[0] = box
+            if box and box[0] <= 0 and box[1] >= rows and box[2] <= 0 and box[3] >= cols:
+                workers.append(None)
+                return
+            for i in range(parts):
+                wk = threading.Thread(target=copy, args=(bounds[i], bounds[i + 1]))
+                wk.start()
+                workers.append(wk)
+
+        hook = getattr(self.core, "on_box", None)
+        if hook is not None:
+            hook(start)
+        else:
+            start()
         try:
             result = device_reset()
-            known[0] = tuple(int(v) for v in result[1])
+            if not workers:  # (a core that never announced the box)
+                start(tuple(int(v) for v in result[1]))
         finally:
+            if hook is not None:
+                hook(None)
             for wk in workers:  # (every read of the caller's `tgt` has completed when reset returns)
-                wk.join()
+                if wk is not None:
+                    wk.join()
         self._tgt = canvas
         self._canvas_stale = True  # the inside of the box is still to come from the device: `tgt` / `step` fetch it
         return result

@@ -74,6 +74,13 @@ def default_device() -> int:
     return 0
 
 
+def _box_callback(fn):
+    """``fn(box tuple)`` as a C callback (a NULL function pointer for ``None``)."""
+    if fn is None:
+        return _lib.BOX_FN()
+    return _lib.BOX_FN(lambda user, p: fn((int(p[0]), int(p[1]), int(p[2]), int(p[3]))))
+
+
 class _Handle:
     def __init__(self):
         self._h = ctypes.c_void_p()
@@ -211,6 +218,12 @@ class GridSolver(_Handle):
             _ptr(box, ctypes.c_int32)))
         self.shape = (int(box[1] - box[0]), int(box[3] - box[2]))
         return int(out_n.value), tuple(int(v) for v in box)
+
+    def on_box(self, fn) -> None:
+        """``fn((x0, x1, y0, y1))`` is called from inside ``reset_from_images`` as soon as the blend's bounding box in
+        the target is known (before the images travel); ``None`` removes it."""
+        self._box_cb = _box_callback(fn)  # (kept alive for as long as the core may call it)
+        _lib.check(self._lib.fpie_b200_grid_on_box(self.handle, self._box_cb, None))
 
     def reset_batch(self, src, mask, tgt, gradient: str = "max") -> None:
         """Batched small edits: ``src`` / ``tgt`` uint8 ``[B, rows, cols, 3]``, ``mask`` uint8
@@ -471,6 +484,11 @@ class EquSolver(_Handle):
         self.N = int(out_n.value)
         self.crop_shape = (int(box[1] - box[0]), int(box[3] - box[2]))
         return self.N, tuple(int(v) for v in box)
+
+    def on_box(self, fn) -> None:
+        """As ``GridSolver.on_box``."""
+        self._box_cb = _box_callback(fn)
+        _lib.check(self._lib.fpie_b200_equ_on_box(self.handle, self._box_cb, None))
 
     def step_paste(self, iteration: int):
         """``step`` + the Processor's scatter (process.py:273-280), on the device:

@@ -310,6 +310,15 @@ int fpie_b200_equ_step_paste_into(fpie_b200_equ *e, int iters, uint8_t *dst, int
 /* Read back the system built by reset_from_images (parity checks). */
 int fpie_b200_equ_system(fpie_b200_equ *e, int32_t *out_A, float *out_X, float *out_B);
 
+/* Early notice of the blend's bounding box.  `*_reset_from_images` uploads the mask first; as soon as its bounding box
+ * is known -- before the source / target rows travel and the system is built -- `cb(user, box4)` is called on the
+ * calling thread with (x0, x1, y0, y1) in TARGET coordinates (what out_box4 returns at the end).  The Processor uses it
+ * to start its private copy of the target (fpie/process.py:268, 384) for what lies outside the box while the device
+ * works.  cb == NULL removes it. */
+typedef void (*fpie_b200_box_fn)(void *user, const int32_t *box4);
+int fpie_b200_grid_on_box(fpie_b200_grid *g, fpie_b200_box_fn cb, void *user);
+int fpie_b200_equ_on_box(fpie_b200_equ *e, fpie_b200_box_fn cb, void *user);
+
 /* Id-range sharding of a general system across devices (fpie_b200/shard.py; the reference's analogue is the MPI
  * EquSolver, fpie/core/mpi/equ.cc:50-59 offsets and 123-146 the exchange -- which moves ALL of X through rank 0 every
  * `min_interval` sweeps; here a rank holds its id range plus `depth` layers of ghost unknowns and only those move).
