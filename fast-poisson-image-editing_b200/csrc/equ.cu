@@ -804,6 +804,7 @@ void EquSolver::reset_from_images(const uint8_t *src, int sh, int sw, const uint
   up.upload(stream_, src, sh, sw, mask, mh, mw, mc, tgt, th, tw, h0, w0, h1, w1, grad_mode);
   const BlendImages &b = up.images();
   const long long count = (long long)b.n * b.m;
+  if (count >= (1ll << 31)) up.wait_copies();  // (the caller's buffers are its own again when this call returns)
   FPIE_REQUIRE(count < (1ll << 31), "reset: crop has more than 2^31 pixels");
   istage_.resize((size_t)count);
   ids_.resize((size_t)count);

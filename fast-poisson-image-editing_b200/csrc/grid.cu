@@ -908,7 +908,12 @@ void GridSolver::reset_from_images(const uint8_t *src, int sh, int sw, const uin
   BlendUpload &up = upload_;  // device copies of the images are kept between resets (no malloc / free per call)
   up.upload(stream_, src, sh, sw, mask, mh, mw, mc, tgt, th, tw, h0, w0, h1, w1, grad_mode, crop, &chunks_);
   batch_ = BatchMap{0, 0, 0, 0};
-  build_from_upload();
+  try {
+    build_from_upload();
+  } catch (...) {
+    up.wait_copies();
+    throw;
+  }
   const BlendImages &b = up.images();
   if (out_n) *out_n = (int64_t)geom_.n * geom_.m;
   if (out_box4) {

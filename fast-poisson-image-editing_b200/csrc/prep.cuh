@@ -64,6 +64,11 @@ class BlendUpload {
   const BlendImages &images() const { return img_; }
   void release();
   void destroy_stream();
+  // block until the row copies of the last upload have left the caller's buffers (error paths: the caller gets its
+  // buffers back when the reset call returns, whatever happened)
+  void wait_copies() {
+    if (copy_stream_) cudaStreamSynchronize(copy_stream_);
+  }
   // called (on the calling thread, from inside `upload`) as soon as the blend's bounding box in TARGET coordinates
   // (x0, x1, y0, y1) is known -- before the source / target rows travel: lets the host prepare its side meanwhile
   void set_box_callback(void (*cb)(void *, const int32_t *), void *user) {

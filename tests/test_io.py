@@ -4,7 +4,6 @@ asynchronous writer whose files equal cv2.imwrite's.  No GPU needed: without a C
 buffers are ordinary arrays."""
 
 import os
-import sys
 import warnings
 
 import numpy as np
