@@ -19,6 +19,17 @@
 
 #include "tma.cuh"
 
+// tuning knobs of the persistent kernel's sweep loop (measured defaults; -D to experiment)
+#ifndef FPIE_PATCH_UNROLL
+#define FPIE_PATCH_UNROLL 2
+#endif
+#ifndef FPIE_PATCH_PULL
+#define FPIE_PATCH_PULL 3
+#endif
+#ifndef FPIE_PATCH_UNROLL_SHORT
+#define FPIE_PATCH_UNROLL_SHORT 2
+#endif
+
 namespace fpie {
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -262,7 +273,8 @@ grid_patch_kernel(PlaneGeom g, BatchMap bm, float *__restrict__ x, const float *
     // last row, the frame columns clear elsewhere -- exactly what was loaded into sel[0] / sel[R-1])
     const uint32_t fsel = (lane == 0 ? 1u : 0u) | (lane == 31 ? 2u : 0u);
     const bool top_frame = !has_up && w == 0, bottom_frame = !has_dn && w == NW - 1;
-#pragma unroll 2
+    constexpr int kPatchUnroll = (R >= 8) ? FPIE_PATCH_UNROLL : FPIE_PATCH_UNROLL_SHORT;
+#pragma unroll kPatchUnroll
     for (int sw = 0; sw < nsweeps; ++sw) {
       const uint32_t poff = (uint32_t)parity * PARITY_BYTES;
       uint64_t *bar = &sm.bar[parity];
@@ -302,7 +314,7 @@ grid_patch_kernel(PlaneGeom g, BatchMap bm, float *__restrict__ x, const float *
       // tall strips pull the neighbours' rows a few interior rows before they are needed -- the barrier has
       // normally completed by then and the shared-memory latency hides behind the remaining rows (+2 % at 8 rows
       // per thread); with 4 rows per thread the barrier has NOT completed that early (-9 %): those wait last
-      constexpr int PULL_ROW = (R >= 8) ? R - 4 : R - 1;
+      constexpr int PULL_ROW = (R >= 8) ? R - FPIE_PATCH_PULL : R - 1;
       auto pull = [&]() {
         mbar_wait(bar, (mphase >> parity) & 1u);
         mphase ^= 1u << parity;
