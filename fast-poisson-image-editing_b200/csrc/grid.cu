@@ -32,6 +32,9 @@ constexpr int kSweepUnroll = FPIE_SWEEP_UNROLL;
 #define FPIE_PULL_AHEAD 4
 #endif
 constexpr int kPullAhead = FPIE_PULL_AHEAD;  // rows before the strip's end at which the neighbours' edge rows are pulled
+#ifndef FPIE_PULL_TALL
+#define FPIE_PULL_TALL 8  // ... for strips of 18 rows and more
+#endif
 
 // ---------------------------------------------------------------------------
 // layout conversion
@@ -296,7 +299,7 @@ __device__ __forceinline__ void tile_sweep_split(float4 (&x)[R], const float4 (&
   float4 up, dn;
   // the neighbours' rows are pulled a few interior rows before they are needed, so that the
   // barrier check and the shared-memory latency hide behind the remaining interior rows
-  constexpr int PULL_ROW = (R >= 18) ? R - 8 : (R >= 8) ? R - kPullAhead : R - 2;
+  constexpr int PULL_ROW = (R >= 18) ? R - FPIE_PULL_TALL : (R >= 8) ? R - kPullAhead : R - 2;
 #pragma unroll
   for (int i = 1; i < R - 1; ++i) {
     if (i == PULL_ROW) {
