@@ -294,8 +294,11 @@ equ_sweep_d16_kernel(long long N, long long pitch, const uint32_t *__restrict__ 
 // D = how many chunks ahead the TABLE entry is fetched (FPIE_B200_D16_DEPTH; 1 is the default: 155 Gupd/s on config 3,
 // two ahead 151).  Only the table entry gates the gathers; B is needed when the sums are formed and is loaded with
 // the chunk's own centre vectors and gathers (prefetching it as well measured the same and costs 6 registers).
+#ifndef FPIE_D16_BLOCK
+#define FPIE_D16_BLOCK 256  // threads per CTA of the persistent gather kernel (1024 threads per SM with the fp16 B stream)
+#endif
 template <bool BH, int D>
-__global__ void __launch_bounds__(256, BH ? 4 : 3)
+__global__ void __launch_bounds__(FPIE_D16_BLOCK, (BH ? 1024 : 768) / FPIE_D16_BLOCK)
 equ_sweep_d16p_kernel(long long N, long long pitch, const uint32_t *__restrict__ D16, const float *__restrict__ B,
                       const __half *__restrict__ B16, const float *__restrict__ xin, float *__restrict__ xout) {
   const long long stride = 4ll * gridDim.x * blockDim.x;
@@ -905,8 +908,11 @@ void EquSolver::sweeps_async(int iters) {
       auto kern = d16_pipe_ ? (b16_ok_ ? (depth == 2 ? equ_sweep_d16p_kernel<true, 2> : equ_sweep_d16p_kernel<true, 1>)
                                        : (depth == 2 ? equ_sweep_d16p_kernel<false, 2> : equ_sweep_d16p_kernel<false, 1>))
                             : (b16_ok_ ? equ_sweep_d16_kernel<true> : equ_sweep_d16_kernel<false>);
-      if (d16_pipe_)  // persistent: d16_ctas_per_sm_ CTAs per SM stride over the system
-        cfg.gridDim = dim3((unsigned)std::min<long long>(cfg.gridDim.x, (long long)sm_count_ * std::min(d16_ctas_per_sm_, b16_ok_ ? 4 : 3)));
+      if (d16_pipe_) {  // persistent: d16_ctas_per_sm_ x 256 threads per SM stride over the system
+        const long long per_sm = (long long)std::min(d16_ctas_per_sm_, b16_ok_ ? 4 : 3) * 256 / FPIE_D16_BLOCK;
+        cfg.blockDim = dim3(FPIE_D16_BLOCK);
+        cfg.gridDim = dim3((unsigned)std::min<long long>(blocks_for((N_ + 3) / 4, FPIE_D16_BLOCK), sm_count_ * std::max(1ll, per_sm)));
+      }
       CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, (long long)N_, (long long)pitch_, d16, b, b16, xin, xout));
     } else if (structured_) {
       const int2 *ud = ud_.ptr;
