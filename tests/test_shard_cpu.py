@@ -136,3 +136,51 @@ def test_gloo_shards_reproduce_global_jacobi(tmp_path, world, depth, steps, labe
         z = np.load(tmp_path / "rank1.npz")
         # a middle rank's ghosts: `depth` layers on each side, each about one image row of unknowns
         assert 0 < int(z["ghosts"]) < 2 * depth * 2 * 41
+
+
+def _tiny_worker(rank, world, port, out_dir):
+    for p in (ROOT, PKG_ROOT, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from band_helpers import OracleEquShardCore
+
+    from fpie_b200 import shard
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # 3 unknowns in a row on 5 ranks: two ranks own nothing (and hold only the constant row)
+        A = np.array([[0, 0, 0, 0], [0, 0, 0, 2], [0, 0, 1, 3], [0, 0, 2, 0]], np.int32)
+        X = np.array([[0, 0, 0], [8, 16, 24], [1, 2, 3], [40, 80, 120]], np.float32)
+        B = np.array([[0, 0, 0], [4, 4, 4], [-2, 0, 2], [9, 9, 9]], np.float32)
+        solver = shard.ShardedEquSolver(OracleEquShardCore(), dist, depth=2)
+        solver.reset(4, A, X, B)
+        img, err = solver.step(7)
+        np.savez(os.path.join(out_dir, f"tiny{rank}.npz"), state=solver.state(), img=img, err=err, lo=solver.plan.lo,
+                 hi=solver.plan.hi)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_more_ranks_than_unknowns_and_a_single_rank(tmp_path):
+    """Empty id ranges (5 ranks, 3 unknowns) still take part in the collectives and return the whole result; one
+    rank alone has no peers and never exchanges."""
+    mp.spawn(_tiny_worker, args=(5, _free_port(), str(tmp_path)), nprocs=5, join=True)
+    A = np.array([[0, 0, 0, 0], [0, 0, 0, 2], [0, 0, 1, 3], [0, 0, 2, 0]], np.int32)
+    X = np.array([[0, 0, 0], [8, 16, 24], [1, 2, 3], [40, 80, 120]], np.float32)
+    B = np.array([[0, 0, 0], [4, 4, 4], [-2, 0, 2], [9, 9, 9]], np.float32)
+    want = np_oracle.equ_sweeps(A, X, B, 7)
+    owned = 0
+    for r in range(5):
+        z = np.load(tmp_path / f"tiny{r}.npz")
+        np.testing.assert_array_equal(z["state"], want)
+        np.testing.assert_array_equal(z["img"][1:], np_oracle.clip_u8(want)[1:])
+        np.testing.assert_allclose(z["err"], np_oracle.equ_residual_f64(A, want, B), rtol=1e-5)
+        owned += int(z["hi"]) - int(z["lo"])
+    assert owned == 3
+    mp.spawn(_worker, args=(1, _free_port(), 4, (9,), "rowmajor", str(tmp_path)), nprocs=1, join=True)
+    n, A, X, B = make_system("holes", (48, 41), 7, "rowmajor")
+    z = np.load(tmp_path / "rank0.npz")
+    np.testing.assert_array_equal(z["state"], np_oracle.equ_sweeps(A, X, B, 9))
+    assert int(z["ghosts"]) == 0 and int(z["sent"]) == 0
