@@ -294,6 +294,16 @@ equ_sweep_d16_kernel(long long N, long long pitch, const uint32_t *__restrict__ 
 // D = how many chunks ahead the TABLE entry is fetched (FPIE_B200_D16_DEPTH; 1 is the default: 155 Gupd/s on config 3,
 // two ahead 151).  Only the table entry gates the gathers; B is needed when the sums are formed and is loaded with
 // the chunk's own centre vectors and gathers (prefetching it as well measured the same and costs 6 registers).
+// read-once streams (table, B) and the written state with streaming cache hints (-DFPIE_D16_STREAM=1: experiment)
+#if defined(FPIE_D16_STREAM) && FPIE_D16_STREAM
+#define D16_LD4(p) __ldcs(p)
+#define D16_LD2(p) __ldcs(p)
+#define D16_ST4(p, v) __stcs(p, v)
+#else
+#define D16_LD4(p) (*(p))
+#define D16_LD2(p) (*(p))
+#define D16_ST4(p, v) (*(p) = (v))
+#endif
 #ifndef FPIE_D16_BLOCK
 #define FPIE_D16_BLOCK 256  // threads per CTA of the persistent gather kernel (1024 threads per SM with the fp16 B stream)
 #endif
@@ -309,19 +319,19 @@ equ_sweep_d16p_kernel(long long N, long long pitch, const uint32_t *__restrict__
 #pragma unroll
   for (int d = 0; d < D; ++d) {
     tq[d] = make_uint4(0u, 0u, 0u, 0u);
-    if (i0 + d * stride < N) tq[d] = *reinterpret_cast<const uint4 *>(D16 + i0 + d * stride);  // (zero-padded to the pitch)
+    if (i0 + d * stride < N) tq[d] = D16_LD4(reinterpret_cast<const uint4 *>(D16 + i0 + d * stride));  // (zero-padded to the pitch)
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
   for (; i0 < N; i0 += stride) {
     const long long inext = i0 + D * stride;
     tq[D] = make_uint4(0u, 0u, 0u, 0u);
-    if (inext < N) tq[D] = *reinterpret_cast<const uint4 *>(D16 + inext);
+    if (inext < N) tq[D] = D16_LD4(reinterpret_cast<const uint4 *>(D16 + inext));
     uint2 bh[3];
     float4 bf[3];
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
       if (BH)
-        bh[ch] = *reinterpret_cast<const uint2 *>(B16 + ch * pitch + i0);
+        bh[ch] = D16_LD2(reinterpret_cast<const uint2 *>(B16 + ch * pitch + i0));
       else
         bf[ch] = ld4(B + ch * pitch + i0);
     }
@@ -359,7 +369,7 @@ equ_sweep_d16p_kernel(long long N, long long pitch, const uint32_t *__restrict__
         o[j] = __fmul_rn(sum, 0.25f);
       }
       if (i0 + 3 < N) {
-        st4(xout + ch * pitch + i0, make_float4(o[0], o[1], o[2], o[3]));
+        D16_ST4(reinterpret_cast<float4 *>(xout + ch * pitch + i0), make_float4(o[0], o[1], o[2], o[3]));
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
