@@ -754,7 +754,6 @@ GridSolver::GridSolver(int device, cudaStream_t stream, int block_k, int variant
   // FPIE_B200_PATCH_ROWS=4|8 overrides the rows per thread
   const char *patch = getenv("FPIE_B200_PATCH");
   patch_off_ = patch && patch[0] == '0';
-  patch_force_ = patch && patch[0] == '2';  // (FPIE_B200_PATCH=2 once forced the kernel for small batches; it is the policy now)
   const char *prow = getenv("FPIE_B200_PATCH_ROWS");
   patch_rows_ = prow ? atoi(prow) : 0;
   if (patch_rows_ != 4 && patch_rows_ != 8) patch_rows_ = 0;

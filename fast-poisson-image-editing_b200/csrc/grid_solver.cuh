@@ -159,7 +159,6 @@ class GridSolver {
   cudaGraphExec_t graph_[2] = {nullptr, nullptr};
   bool graph_off_ = false, graph_warm_ = false;
   bool patch_off_ = false;      // persistent small-image kernel disabled
-  bool patch_force_ = false;    // ... used even when too few items run side by side for it to pay
   int patch_rows_ = 0;          // rows per thread override (0 = automatic)
   int patch_min_iters_ = 32;    // shorter runs stay on the tiled kernel (the persistent launch reads and writes the planes once)
   int64_t patch_launches_ = 0;

@@ -112,7 +112,7 @@ def _full_batch(b, n, m, seed):
 def test_persistent_kernel_matches_oracle_and_mosaic(b, n, m, iters, full, monkeypatch):
     import fpie_b200
 
-    monkeypatch.setenv("FPIE_B200_PATCH", "2")  # (also for batches too small for the kernel to pay)
+    monkeypatch.setenv("FPIE_B200_PATCH", "2")  # (any value but "0": on -- the kernel is the policy for every small image it fits)
     src, mask, tgt = _full_batch(b, n, m, seed=n + m) if full else _batch(b, n, m, seed=n + m)
     proc = fpie_b200.BatchGridProcessor("max", "b200")
     proc.reset(src, mask, tgt)
@@ -153,7 +153,7 @@ def test_persistent_kernel_single_images(kind, n, m, rows, monkeypatch):
     from fpie_b200 import synth
 
     monkeypatch.setenv("FPIE_B200_PATCH_ROWS", rows)
-    monkeypatch.setenv("FPIE_B200_PATCH", "2")  # a single image stays on the tiled kernel unless forced
+    monkeypatch.setenv("FPIE_B200_PATCH", "2")  # (on; single small images take the persistent kernel by policy)
     src, mask, tgt = synth.make_problem(kind, n, m, seed=7)
     proc = fpie_b200.GridProcessor("avg", "b200")
     proc.reset(src, mask, tgt, (0, 0), (0, 0))
